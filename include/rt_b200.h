@@ -148,7 +148,8 @@ typedef struct rt_config {
     int32_t band_rows;      /* RT_SPLIT_TILES: rows per band, bands dealt round-robin; 0 = 8     */
     int32_t instrument;     /* 1 = count node visits / triangle tests per segment (slower build
                                of the same kernels; never used for timed runs)                   */
-    int32_t reserved0;
+    int32_t kernel_timing;  /* 1 = bracket every kernel with CUDA events on the ctx stream and report
+                               per-class device time through rt_get_counters (small overhead)    */
     uint64_t max_paths_in_flight; /* path slots kept resident; 0 = auto                          */
 } rt_config;
 
@@ -164,6 +165,7 @@ typedef struct rt_counters {
     double build_ms;        /* device time of the last rt_scene_build                            */
     uint64_t bvh_nodes;     /* inner nodes of the LBVH                                           */
     uint64_t bvh_bytes;     /* bytes of node + triangle arrays traversal reads                   */
+    uint64_t bvh_depth;     /* longest leaf-to-root path of the LBVH                             */
 } rt_counters;
 
 /* Host view of the GPU-built BVH, for validation only (tests check that every triangle lies in
@@ -233,6 +235,15 @@ int rt_screenshot(rt_ctx* ctx, const rt_uniforms* uniforms, int32_t frames, uint
  * device-resident throughput.  rt_screenshot_fetch copies the last result out. */
 int rt_screenshot_device(rt_ctx* ctx, const rt_uniforms* uniforms, int32_t frames);
 int rt_screenshot_fetch(rt_ctx* ctx, uint8_t* rgb8_topdown);
+
+/* The multi-GPU pieces of rt_screenshot, exposed so that ranks can also be emulated one after the
+ * other on a single GPU: render this rank's share into the 8-bit frame sums (W*H*3 u32, row 0 =
+ * bottom, zero where the rank owns nothing), read them, and finalise any summed buffer
+ * (rayTracing.cpp:248-259). */
+int rt_screenshot_partial(rt_ctx* ctx, const rt_uniforms* uniforms, int32_t frames);
+int rt_read_frame_sum(rt_ctx* ctx, uint32_t* sums_bottom_up);
+int rt_finalize_sums(rt_ctx* ctx, const uint32_t* sums_bottom_up, int32_t width, int32_t height,
+                     int32_t frames, uint8_t* rgb8_topdown);
 
 /* ---------------------------------------------------------------- parity hooks */
 /* Closest hit of the primary ray of every pixel: tri_id[y*W+x] = index into the array given to

@@ -1016,15 +1016,15 @@ void orc_camera_uniforms(int32_t width, int32_t height, const float pos[3], floa
                          rt_uniforms* out) {
     const float aspect = (float)width / (float)height;  // C:102
     V3 front;
-    front.x = (float)(cos(yaw) * cos(pitch));  // C:152-154
-    front.y = (float)sin(pitch);
-    front.z = (float)(sin(yaw) * cos(pitch));
+    front.x = std::cos(yaw) * std::cos(pitch);  // C:152-154 (float overloads)
+    front.y = std::sin(pitch);
+    front.z = std::sin(yaw) * std::cos(pitch);
     front = normalize(front);
     const V3 worldUp = v3(0, 1, 0);
     const V3 right = normalize(cross(worldUp, front));
     const V3 up = normalize(cross(front, right));
     const float h = std::tan(hfov / 2);
-    const float viewportWidth = 2 * h / (float)exp(zoom * 0.1f);
+    const float viewportWidth = 2 * h / std::exp(zoom * 0.1f);
     const float viewportHeight = viewportWidth / aspect;
     const V3 viewportRight = (right * viewportWidth) * focusDistance;
     const V3 viewportUp = (up * viewportHeight) * focusDistance;

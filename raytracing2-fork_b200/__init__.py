@@ -65,7 +65,7 @@ FIRST_HIT_CENTRE, FIRST_HIT_SAMPLE0 = 0, 1
 class Config(C.Structure):
     _fields_ = [("device", C.c_int32), ("rng_mode", C.c_int32), ("split_mode", C.c_int32),
                 ("rank", C.c_int32), ("world_size", C.c_int32), ("band_rows", C.c_int32),
-                ("instrument", C.c_int32), ("reserved0", C.c_int32),
+                ("instrument", C.c_int32), ("kernel_timing", C.c_int32),
                 ("max_paths_in_flight", C.c_uint64)]
 
 
@@ -73,7 +73,8 @@ class Counters(C.Structure):
     _fields_ = [("segments", C.c_uint64), ("paths", C.c_uint64), ("node_visits", C.c_uint64),
                 ("tri_tests", C.c_uint64), ("extend_launches", C.c_uint64),
                 ("kernel_launches", C.c_uint64), ("extend_ms", C.c_double), ("shade_ms", C.c_double),
-                ("build_ms", C.c_double), ("bvh_nodes", C.c_uint64), ("bvh_bytes", C.c_uint64)]
+                ("build_ms", C.c_double), ("bvh_nodes", C.c_uint64), ("bvh_bytes", C.c_uint64),
+                ("bvh_depth", C.c_uint64)]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}
@@ -170,7 +171,7 @@ ABI_SYMBOLS = [
     "rt_create", "rt_destroy", "rt_last_error", "rt_version", "rt_set_stream",
     "rt_scene_set_triangles", "rt_scene_set_materials", "rt_scene_set_texture", "rt_scene_build",
     "rt_render_frame", "rt_read_frame_rgba32f", "rt_screenshot", "rt_screenshot_device",
-    "rt_screenshot_fetch", "rt_first_hit", "rt_trace_rays", "rt_scene_get_bvh", "rt_get_counters",
+    "rt_screenshot_fetch", "rt_screenshot_partial", "rt_read_frame_sum", "rt_finalize_sums", "rt_first_hit", "rt_trace_rays", "rt_scene_get_bvh", "rt_get_counters",
     "rt_reset_counters", "rt_comm_unique_id", "rt_comm_init", "rt_split_rows", "rt_split_frames",
 ]
 
@@ -351,9 +352,10 @@ class Backend:
     (rayTracing.cpp:1293, :1323-1325, :1402-1406, :124-283) through the C-ABI."""
 
     def __init__(self, device=0, rng_mode=RNG_PHILOX, split_mode=SPLIT_NONE, rank=0, world_size=1,
-                 band_rows=0, instrument=False, max_paths_in_flight=0):
+                 band_rows=0, instrument=False, kernel_timing=False, max_paths_in_flight=0):
         self.L = backend_lib()
-        cfg = Config(device, rng_mode, split_mode, rank, world_size, band_rows, int(instrument), 0,
+        cfg = Config(device, rng_mode, split_mode, rank, world_size, band_rows, int(instrument),
+                     int(kernel_timing),
                      max_paths_in_flight)
         self.cfg = cfg
         self.h = C.c_void_p()
@@ -432,6 +434,22 @@ class Backend:
     def screenshot_fetch(self) -> np.ndarray:
         out = np.zeros((self.height, self.width, 3), dtype=np.uint8)
         self._chk(self.L.rt_screenshot_fetch(self.h, _ptr(out)))
+        return out
+
+    def screenshot_partial(self, u: np.ndarray, frames: int) -> np.ndarray:
+        """This rank's share of a screenshot: the 8-bit frame sums (H, W, 3) u32, row 0 = bottom."""
+        u = np.ascontiguousarray(u, dtype=UNIFORMS)
+        self.width, self.height = int(u["width"][0]), int(u["height"][0])
+        self._chk(self.L.rt_screenshot_partial(self.h, _ptr(u), C.c_int32(frames)))
+        sums = np.zeros((self.height, self.width, 3), dtype=np.uint32)
+        self._chk(self.L.rt_read_frame_sum(self.h, _ptr(sums)))
+        return sums
+
+    def finalize_sums(self, sums: np.ndarray, frames: int) -> np.ndarray:
+        sums = np.ascontiguousarray(sums, dtype=np.uint32)
+        h, w = sums.shape[:2]
+        out = np.zeros((h, w, 3), dtype=np.uint8)
+        self._chk(self.L.rt_finalize_sums(self.h, _ptr(sums), w, h, C.c_int32(frames), _ptr(out)))
         return out
 
     def first_hit(self, u: np.ndarray, mode=FIRST_HIT_CENTRE):

@@ -1,0 +1,410 @@
+// bvh_build.cu — LBVH construction on the GPU (replaces the reference's CPU builder,
+// RayTracing/Assets/headers/BVH.h:145-221, called at RayTracing/src/rayTracing.cpp:1293).
+//
+// Pipeline (all on the ctx stream, no host round trips apart from one 4-byte depth read-back):
+//   k_tri_bounds   per-triangle AABB + centroid, scene centroid bounds by warp shuffle + atomics
+//   k_morton       63-bit Morton code of the centroid (21 bits / axis)
+//   radix sort     hand-written stable LSD sort of (code, index): 8 passes x 8 bits, each pass
+//                  = histogram (k_hist) -> exclusive scan over [digit][block] (k_scan) -> stable
+//                  scatter with warp match-any ranking (k_scatter)
+//   k_hierarchy    Karras 2012: one thread per inner node finds its range and split
+//   k_refit        bottom-up AABB union with one atomic flag per inner node
+//   k_emit_nodes   64-byte nodes with both child boxes in the parent
+//   k_emit_tris    sorted triangle records: (a, e0, e1, N) | (uvs, material, orig)
+// Everything is deterministic (stable sort, min/max are order independent), so every GPU of a
+// multi-GPU job builds the identical tree.
+#include "rt_internal.h"
+
+namespace rt {
+
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t f2ord(float f) {  // order-preserving float → uint
+    const uint32_t u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float ord2f(uint32_t u) {
+    return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u);
+}
+
+// bounds[0..2] = min of centroids, [3..5] = max of centroids, [6..8] = scene min, [9..11] = scene max
+// (order-preserving uints)
+__global__ void k_init_bounds(uint32_t* bounds) {
+    const int i = threadIdx.x;
+    if (i < 12) bounds[i] = ((i % 6) < 3) ? 0xffffffffu : 0u;
+}
+
+__global__ void __launch_bounds__(256) k_tri_bounds(const rt_triangle* __restrict__ tris, int n,
+                                                    float4* __restrict__ centroid,
+                                                    uint32_t* __restrict__ bounds) {
+    float cmin[3] = {3.4e38f, 3.4e38f, 3.4e38f}, cmax[3] = {-3.4e38f, -3.4e38f, -3.4e38f};
+    float smin[3] = {3.4e38f, 3.4e38f, 3.4e38f}, smax[3] = {-3.4e38f, -3.4e38f, -3.4e38f};
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const float4 a = *reinterpret_cast<const float4*>(tris[i].a);
+        const float4 b = *reinterpret_cast<const float4*>(tris[i].b);
+        const float4 c = *reinterpret_cast<const float4*>(tris[i].c);
+        const float lo[3] = {fminf(fminf(a.x, b.x), c.x), fminf(fminf(a.y, b.y), c.y), fminf(fminf(a.z, b.z), c.z)};
+        const float hi[3] = {fmaxf(fmaxf(a.x, b.x), c.x), fmaxf(fmaxf(a.y, b.y), c.y), fmaxf(fmaxf(a.z, b.z), c.z)};
+        float ce[3];
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            ce[k] = 0.5f * lo[k] + 0.5f * hi[k];
+            cmin[k] = fminf(cmin[k], ce[k]);
+            cmax[k] = fmaxf(cmax[k], ce[k]);
+            smin[k] = fminf(smin[k], lo[k]);
+            smax[k] = fmaxf(smax[k], hi[k]);
+        }
+        centroid[i] = make_float4(ce[0], ce[1], ce[2], 0.0f);
+    }
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            cmin[k] = fminf(cmin[k], __shfl_xor_sync(0xffffffffu, cmin[k], off));
+            cmax[k] = fmaxf(cmax[k], __shfl_xor_sync(0xffffffffu, cmax[k], off));
+            smin[k] = fminf(smin[k], __shfl_xor_sync(0xffffffffu, smin[k], off));
+            smax[k] = fmaxf(smax[k], __shfl_xor_sync(0xffffffffu, smax[k], off));
+        }
+    }
+    if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            atomicMin(&bounds[k], f2ord(cmin[k]));
+            atomicMax(&bounds[3 + k], f2ord(cmax[k]));
+            atomicMin(&bounds[6 + k], f2ord(smin[k]));
+            atomicMax(&bounds[9 + k], f2ord(smax[k]));
+        }
+    }
+}
+
+__device__ __forceinline__ uint64_t spread21(uint32_t v) {  // 21 bits → every third bit
+    uint64_t x = v & 0x1fffffu;
+    x = (x | x << 32) & 0x1f00000000ffffull;
+    x = (x | x << 16) & 0x1f0000ff0000ffull;
+    x = (x | x << 8) & 0x100f00f00f00f00full;
+    x = (x | x << 4) & 0x10c30c30c30c30c3ull;
+    x = (x | x << 2) & 0x1249249249249249ull;
+    return x;
+}
+
+__global__ void __launch_bounds__(256) k_morton(const float4* __restrict__ centroid, int n,
+                                                const uint32_t* __restrict__ bounds,
+                                                uint64_t* __restrict__ keys, uint32_t* __restrict__ vals) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float4 c = centroid[i];
+    const float cc[3] = {c.x, c.y, c.z};
+    uint32_t q[3];
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        const float lo = ord2f(bounds[k]), hi = ord2f(bounds[3 + k]);
+        const float ext = hi - lo;
+        float t = ext > 0.0f ? (cc[k] - lo) / ext : 0.0f;
+        t = fminf(fmaxf(t, 0.0f), 1.0f);
+        q[k] = min((uint32_t)(t * 2097152.0f), 2097151u);
+    }
+    keys[i] = (spread21(q[0]) << 2) | (spread21(q[1]) << 1) | spread21(q[2]);
+    vals[i] = (uint32_t)i;
+}
+
+// --------------------------------------------------------------------------------------------- radix sort
+constexpr int kSortThreads = 256;
+constexpr int kSortItems = 8;                                // keys per thread
+constexpr int kSortTile = kSortThreads * kSortItems;         // 2048 keys per block
+constexpr int kSortWarps = kSortThreads / 32;
+
+__global__ void __launch_bounds__(kSortThreads) k_hist(const uint64_t* __restrict__ keys, int n, int shift,
+                                                       uint32_t* __restrict__ hist, int nblocks) {
+    __shared__ uint32_t h[256];
+    h[threadIdx.x] = 0;
+    __syncthreads();
+    const int base = blockIdx.x * kSortTile;
+#pragma unroll
+    for (int k = 0; k < kSortItems; k++) {
+        const int i = base + k * kSortThreads + threadIdx.x;
+        if (i < n) atomicAdd(&h[(uint32_t)(keys[i] >> shift) & 255u], 1u);
+    }
+    __syncthreads();
+    hist[threadIdx.x * nblocks + blockIdx.x] = h[threadIdx.x];  // digit-major
+}
+
+// exclusive scan of the digit-major histogram (256 * nblocks entries) by a single block: enough for
+// ~10^7 keys (nblocks ~ 5000 → 1.3 M entries, <100 us), and it keeps the pass deterministic.
+__global__ void __launch_bounds__(1024) k_scan(uint32_t* __restrict__ hist, int total) {
+    __shared__ uint32_t warpSums[32];
+    __shared__ uint32_t carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (int base = 0; base < total; base += 1024 * 4) {
+        const int i0 = base + threadIdx.x * 4;
+        uint32_t v[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) v[k] = (i0 + k < total) ? hist[i0 + k] : 0u;
+        const uint32_t mine = v[0] + v[1] + v[2] + v[3];
+        uint32_t incl = mine;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, incl, off);
+            if ((threadIdx.x & 31) >= off) incl += t;
+        }
+        if ((threadIdx.x & 31) == 31) warpSums[threadIdx.x >> 5] = incl;
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            uint32_t w = warpSums[threadIdx.x];
+#pragma unroll
+            for (int off = 1; off < 32; off <<= 1) {
+                const uint32_t t = __shfl_up_sync(0xffffffffu, w, off);
+                if (threadIdx.x >= off) w += t;
+            }
+            warpSums[threadIdx.x] = w;
+        }
+        __syncthreads();
+        const uint32_t warpBase = (threadIdx.x >> 5) ? warpSums[(threadIdx.x >> 5) - 1] : 0u;
+        uint32_t run = carry + warpBase + incl - mine;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            if (i0 + k < total) hist[i0 + k] = run;
+            run += v[k];
+        }
+        __syncthreads();
+        if (threadIdx.x == 1023) carry = run;
+        __syncthreads();
+    }
+}
+
+// Stable scatter.  Key order inside a block is (warp, item, lane): warp w owns the contiguous strip
+// [w*256, (w+1)*256) of the tile and walks it 32 keys at a time, so ranking by (earlier warps,
+// earlier items of my warp, lower lanes) preserves the input order of equal digits.
+__global__ void __launch_bounds__(kSortThreads) k_scatter(const uint64_t* __restrict__ keysIn,
+                                                          const uint32_t* __restrict__ valsIn,
+                                                          uint64_t* __restrict__ keysOut,
+                                                          uint32_t* __restrict__ valsOut, int n, int shift,
+                                                          const uint32_t* __restrict__ hist, int nblocks) {
+    __shared__ uint32_t warpCount[kSortWarps][256];
+    __shared__ uint32_t digitBase[256];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int d = lane; d < 256; d += 32) warpCount[warp][d] = 0;
+    digitBase[threadIdx.x] = hist[threadIdx.x * nblocks + blockIdx.x];
+    __syncwarp();
+
+    const int stripBase = blockIdx.x * kSortTile + warp * (32 * kSortItems);
+    uint64_t key[kSortItems];
+    uint32_t rank[kSortItems];
+#pragma unroll
+    for (int k = 0; k < kSortItems; k++) {
+        const int i = stripBase + k * 32 + lane;
+        const bool valid = i < n;
+        key[k] = valid ? keysIn[i] : ~0ull;
+        const uint32_t digit = (uint32_t)(key[k] >> shift) & 255u;
+        // invalid lanes vote in a private group so they never disturb real digits
+        const uint32_t peers = __match_any_sync(0xffffffffu, valid ? digit : 256u + lane);
+        const uint32_t below = __popc(peers & ((1u << lane) - 1u));
+        uint32_t base = 0;
+        if (valid) {
+            const int leader = __ffs(peers) - 1;
+            if (lane == leader) {
+                base = warpCount[warp][digit];
+                warpCount[warp][digit] = base + __popc(peers);
+            }
+            base = __shfl_sync(peers, base, leader);
+        }
+        rank[k] = base + below;
+        __syncwarp();
+    }
+    __syncthreads();
+    // exclusive prefix over warps, per digit (thread d handles digit d)
+    {
+        uint32_t run = digitBase[threadIdx.x];
+#pragma unroll
+        for (int w = 0; w < kSortWarps; w++) {
+            const uint32_t c = warpCount[w][threadIdx.x];
+            warpCount[w][threadIdx.x] = run;
+            run += c;
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < kSortItems; k++) {
+        const int i = stripBase + k * 32 + lane;
+        if (i < n) {
+            const uint32_t digit = (uint32_t)(key[k] >> shift) & 255u;
+            const uint32_t pos = warpCount[warp][digit] + rank[k];
+            keysOut[pos] = key[k];
+            valsOut[pos] = valsIn[i];
+        }
+    }
+}
+
+// The histogram kernel must bin keys with the same (warp, item, lane) → block mapping only at block
+// granularity, which it does: both kernels give block b the keys [b*2048, (b+1)*2048).
+
+// --------------------------------------------------------------------------------------------- Karras
+__device__ __forceinline__ int delta(const uint64_t* __restrict__ keys, int n, int i, int j) {
+    if (j < 0 || j >= n) return -1;
+    const uint64_t a = keys[i], b = keys[j];
+    if (a == b) return 64 + __clz((uint32_t)i ^ (uint32_t)j);
+    return __clzll((long long)(a ^ b));
+}
+
+// children[2*i], children[2*i+1]: >= 0 inner node, < 0 leaf ~slot.  parent[node] for inner nodes,
+// parent[n-1+slot] for leaves.
+__global__ void __launch_bounds__(256) k_hierarchy(const uint64_t* __restrict__ keys, int n,
+                                                   int32_t* __restrict__ children,
+                                                   int32_t* __restrict__ parent) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n - 1) return;
+    const int d = (delta(keys, n, i, i + 1) - delta(keys, n, i, i - 1)) >= 0 ? 1 : -1;
+    const int dmin = delta(keys, n, i, i - d);
+    int lmax = 2;
+    while (delta(keys, n, i, i + lmax * d) > dmin) lmax <<= 1;
+    int l = 0;
+    for (int t = lmax >> 1; t >= 1; t >>= 1)
+        if (delta(keys, n, i, i + (l + t) * d) > dmin) l += t;
+    const int j = i + l * d;
+    const int dnode = delta(keys, n, i, j);
+    int s = 0;
+    int t = l;
+    do {
+        t = (t + 1) >> 1;
+        if (delta(keys, n, i, i + (s + t) * d) > dnode) s += t;
+    } while (t > 1);
+    const int gamma = i + s * d + min(d, 0);
+    const int lo = min(i, j), hi = max(i, j);
+    const int32_t left = (lo == gamma) ? ~gamma : gamma;
+    const int32_t right = (hi == gamma + 1) ? ~(gamma + 1) : (gamma + 1);
+    children[2 * i] = left;
+    children[2 * i + 1] = right;
+    if (left >= 0) parent[left] = i; else parent[n - 1 + gamma] = i;
+    if (right >= 0) parent[right] = i; else parent[n - 1 + gamma + 1] = i;
+    if (i == 0) parent[0] = -1;
+}
+
+// boxes: 2 float4 per entity (lo, hi); entities 0..n-2 inner nodes, n-1.. leaves (by sorted slot)
+__global__ void __launch_bounds__(256) k_refit(const rt_triangle* __restrict__ tris,
+                                               const uint32_t* __restrict__ sortedIdx, int n,
+                                               const uint32_t* __restrict__ bounds,
+                                               const int32_t* __restrict__ children,
+                                               const int32_t* __restrict__ parent,
+                                               float4* __restrict__ boxes, uint32_t* __restrict__ flags,
+                                               uint32_t* __restrict__ maxDepth) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n) return;
+    const rt_triangle& t = tris[sortedIdx[s]];
+    // Leaf boxes are padded like the reference's (BVH.h:47-51, 1e-4) and by 2e-6 of the scene extent:
+    // the exact triangle test and the slab test round differently, the pad keeps every accepted hit
+    // strictly inside its leaf's slabs.
+    float ext = 0.0f;
+#pragma unroll
+    for (int k = 0; k < 3; k++) ext = fmaxf(ext, ord2f(bounds[9 + k]) - ord2f(bounds[6 + k]));
+    const float pad = fmaxf(1e-4f, 2e-6f * ext);
+    float lo[3], hi[3];
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        lo[k] = fminf(fminf(t.a[k], t.b[k]), t.c[k]) - pad;
+        hi[k] = fmaxf(fmaxf(t.a[k], t.b[k]), t.c[k]) + pad;
+    }
+    boxes[2 * (n - 1 + s)] = make_float4(lo[0], lo[1], lo[2], 0.0f);
+    boxes[2 * (n - 1 + s) + 1] = make_float4(hi[0], hi[1], hi[2], 0.0f);
+    if (n == 1) return;
+    __threadfence();
+    int node = parent[n - 1 + s];
+    uint32_t depth = 1;
+    while (node >= 0) {
+        if (atomicAdd(&flags[node], 1u) == 0u) return;  // first arrival: the sibling is not ready yet
+        __threadfence();
+        const int32_t cl = children[2 * node], cr = children[2 * node + 1];
+        const int el = cl >= 0 ? cl : (n - 1 + ~cl), er = cr >= 0 ? cr : (n - 1 + ~cr);
+        // the sibling's box was written by another SM: read through L2, never a stale L1 line
+        const float4 llo = __ldcg(&boxes[2 * el]);
+        const float4 lhi = __ldcg(&boxes[2 * el + 1]);
+        const float4 rlo = __ldcg(&boxes[2 * er]);
+        const float4 rhi = __ldcg(&boxes[2 * er + 1]);
+        boxes[2 * node] = make_float4(fminf(llo.x, rlo.x), fminf(llo.y, rlo.y), fminf(llo.z, rlo.z), 0.0f);
+        boxes[2 * node + 1] = make_float4(fmaxf(lhi.x, rhi.x), fmaxf(lhi.y, rhi.y), fmaxf(lhi.z, rhi.z), 0.0f);
+        __threadfence();
+        node = parent[node];
+        depth++;
+    }
+    atomicMax(maxDepth, depth);
+}
+
+__global__ void __launch_bounds__(256) k_emit_nodes(int n, const int32_t* __restrict__ children,
+                                                    const float4* __restrict__ boxes,
+                                                    float4* __restrict__ nodes) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n - 1) return;
+    const int32_t cl = children[2 * i], cr = children[2 * i + 1];
+    const int el = cl >= 0 ? cl : (n - 1 + ~cl), er = cr >= 0 ? cr : (n - 1 + ~cr);
+    const float4 llo = boxes[2 * el], lhi = boxes[2 * el + 1];
+    const float4 rlo = boxes[2 * er], rhi = boxes[2 * er + 1];
+    const int32_t pl = cl >= 0 ? cl : pack_leaf(~cl, 1);
+    const int32_t pr = cr >= 0 ? cr : pack_leaf(~cr, 1);
+    nodes[4 * i + 0] = make_float4(llo.x, lhi.x, llo.y, lhi.y);
+    nodes[4 * i + 1] = make_float4(rlo.x, rhi.x, rlo.y, rhi.y);
+    nodes[4 * i + 2] = make_float4(llo.z, lhi.z, rlo.z, rhi.z);
+    nodes[4 * i + 3] = make_float4(__int_as_float(pl), __int_as_float(pr), 0.0f, 0.0f);
+}
+
+// Sorted triangle records.  e0, e1 and N are computed with exactly the operations of
+// compute.glsl:307-309 (and -fmad=false), so precomputing them changes no bit of any hit.
+__global__ void __launch_bounds__(256) k_emit_tris(const rt_triangle* __restrict__ tris,
+                                                   const uint32_t* __restrict__ sortedIdx, int n,
+                                                   float4* __restrict__ geom, float4* __restrict__ shade,
+                                                   int32_t* __restrict__ orig) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n) return;
+    const uint32_t src = sortedIdx[s];
+    const rt_triangle& t = tris[src];
+    const V3 a = v3(t.a), b = v3(t.b), c = v3(t.c);
+    const V3 e0 = b - a, e1 = c - a;
+    const V3 N = cross(e0, e1);
+    geom[3 * s + 0] = make_float4(a.x, a.y, a.z, e0.x);
+    geom[3 * s + 1] = make_float4(e0.y, e0.z, e1.x, e1.y);
+    geom[3 * s + 2] = make_float4(e1.z, N.x, N.y, N.z);
+    shade[2 * s + 0] = make_float4(t.aTex[0], t.aTex[1], t.bTex[0], t.bTex[1]);
+    shade[2 * s + 1] = make_float4(t.cTex[0], t.cTex[1], __int_as_float(t.materialIndex), __int_as_float((int32_t)src));
+    orig[s] = (int32_t)src;
+}
+
+__global__ void k_iota(uint32_t* v, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) v[i] = (uint32_t)i;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Host driver.  Returns the tree depth through *depthOut (one small D2H after the build).
+cudaError_t build_lbvh(const BuildArgs& a, cudaStream_t st, uint64_t* launches) {
+    const int n = a.n;
+    auto nb = [](int count, int per) { return (count + per - 1) / per; };
+    uint64_t L = 0;
+    k_init_bounds<<<1, 32, 0, st>>>(a.bounds); L++;
+    k_tri_bounds<<<min(nb(n, 256), 148 * 8), 256, 0, st>>>(a.tris, n, a.centroid, a.bounds); L++;
+    cudaMemsetAsync(a.maxDepth, 0, sizeof(uint32_t), st);
+    if (n >= 2) {
+        k_morton<<<nb(n, 256), 256, 0, st>>>(a.centroid, n, a.bounds, a.keys[0], a.vals[0]); L++;
+        const int nblocks = nb(n, kSortTile);
+        int cur = 0;
+        for (int pass = 0; pass < 8; pass++) {
+            const int shift = pass * 8;
+            k_hist<<<nblocks, kSortThreads, 0, st>>>(a.keys[cur], n, shift, a.hist, nblocks); L++;
+            k_scan<<<1, 1024, 0, st>>>(a.hist, 256 * nblocks); L++;
+            k_scatter<<<nblocks, kSortThreads, 0, st>>>(a.keys[cur], a.vals[cur], a.keys[cur ^ 1],
+                                                        a.vals[cur ^ 1], n, shift, a.hist, nblocks); L++;
+            cur ^= 1;
+        }
+        // 8 passes: the result is back in buffer 0
+        k_hierarchy<<<nb(n - 1, 256), 256, 0, st>>>(a.keys[0], n, a.children, a.parent); L++;
+        cudaMemsetAsync(a.flags, 0, sizeof(uint32_t) * (size_t)(n - 1), st);
+    } else {
+        k_iota<<<1, 32, 0, st>>>(a.vals[0], n); L++;
+    }
+    k_refit<<<nb(n, 256), 256, 0, st>>>(a.tris, a.vals[0], n, a.bounds, a.children, a.parent, a.boxes, a.flags,
+                                        a.maxDepth); L++;
+    if (n >= 2) { k_emit_nodes<<<nb(n - 1, 256), 256, 0, st>>>(n, a.children, a.boxes, a.nodes); L++; }
+    k_emit_tris<<<nb(n, 256), 256, 0, st>>>(a.tris, a.vals[0], n, a.geom, a.shade, a.orig); L++;
+    if (launches) *launches += L;
+    return cudaGetLastError();
+}
+
+size_t sort_hist_entries(int n) { return (size_t)256 * ((n + kSortTile - 1) / kSortTile); }
+
+}  // namespace rt

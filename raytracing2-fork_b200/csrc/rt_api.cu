@@ -1,0 +1,851 @@
+// rt_api.cu — the C-ABI of include/rt_b200.h: context, device memory, frame / screenshot drivers,
+// multi-GPU exchange.  One ctx = one GPU; all work is enqueued on one stream (the ctx's own
+// non-blocking stream or the caller's, rt_set_stream).  No exception leaves this file.
+#include <dlfcn.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "rt_internal.h"
+
+using namespace rt;
+
+namespace {
+
+// ---------------------------------------------------------------------------------------------- NCCL (dlopen)
+// Minimal declarations of the stable NCCL C API; the library is resolved at run time so that a
+// process that already carries NCCL (torch) shares its copy and a process without multi-GPU work
+// never needs it.
+typedef struct ncclComm* ncclComm_t;
+typedef struct { char internal[128]; } ncclUniqueId;
+typedef int ncclResult_t;
+enum { ncclUint32 = 3, ncclSum = 0 };
+struct NcclApi {
+    void* handle = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*Reduce)(const void*, void*, size_t, int, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Send)(const void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Recv)(void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+    bool ok = false;
+    std::string err;
+};
+NcclApi& nccl() {
+    static NcclApi api;
+    static bool tried = false;
+    if (tried) return api;
+    tried = true;
+    const char* names[] = {"libnccl.so.2", "libnccl.so"};
+    for (const char* n : names) {
+        api.handle = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+        if (api.handle) break;
+    }
+    if (!api.handle) {
+        api.err = std::string("cannot dlopen libnccl.so.2: ") + (dlerror() ? dlerror() : "?");
+        return api;
+    }
+    auto sym = [&](const char* s) { return dlsym(api.handle, s); };
+    api.GetUniqueId = (decltype(api.GetUniqueId))sym("ncclGetUniqueId");
+    api.CommInitRank = (decltype(api.CommInitRank))sym("ncclCommInitRank");
+    api.CommDestroy = (decltype(api.CommDestroy))sym("ncclCommDestroy");
+    api.Reduce = (decltype(api.Reduce))sym("ncclReduce");
+    api.Send = (decltype(api.Send))sym("ncclSend");
+    api.Recv = (decltype(api.Recv))sym("ncclRecv");
+    api.GroupStart = (decltype(api.GroupStart))sym("ncclGroupStart");
+    api.GroupEnd = (decltype(api.GroupEnd))sym("ncclGroupEnd");
+    api.GetErrorString = (decltype(api.GetErrorString))sym("ncclGetErrorString");
+    api.ok = api.GetUniqueId && api.CommInitRank && api.CommDestroy && api.Reduce && api.Send && api.Recv &&
+             api.GroupStart && api.GroupEnd;
+    if (!api.ok) api.err = "libnccl.so.2 lacks a required symbol";
+    return api;
+}
+
+// ---------------------------------------------------------------------------------------------- device buffers
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        cudaError_t e = cudaMalloc(&p, bytes ? bytes : 16);
+        if (e == cudaSuccess) cap = bytes;
+        return e;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+    template <class T>
+    T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+thread_local std::string g_static_err = "";
+constexpr int kEventCap = 16384;
+constexpr int kMaxBounces = 4096;
+
+}  // namespace
+
+struct rt_ctx {
+    rt_config cfg{};
+    int sm_count = 148;
+    cudaStream_t own_stream = nullptr;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    int sticky = RT_OK;
+
+    // host copies (kept so that rt_scene_build can be repeated and for validation)
+    int64_t n_tris = 0;
+    int32_t n_mats = 0;
+    bool built = false;
+    int32_t max_mat_index = -1;
+    uint32_t bvh_depth = 0;
+
+    DevBuf d_tris, d_mats, d_tex[RT_MAX_TEXTURES];
+    int tex_w[RT_MAX_TEXTURES] = {0}, tex_h[RT_MAX_TEXTURES] = {0}, tex_ch[RT_MAX_TEXTURES] = {0};
+    // build scratch + outputs
+    DevBuf d_centroid, d_bounds, d_keys[2], d_vals[2], d_hist, d_children, d_parent, d_boxes, d_flags, d_depth;
+    DevBuf d_nodes, d_geom, d_shade, d_orig;
+    // wavefront
+    DevBuf d_path[6], d_hit, d_contrib, d_accum, d_pixrng, d_counts, d_stats, d_image, d_sum, d_out, d_rows;
+    DevBuf d_stage, d_compact;  // tile-split gather
+    DevBuf d_scratch[6];        // first-hit / trace-rays staging
+    int width = 0, height = 0;
+    std::vector<int32_t> rows;  // rows this rank owns (tile split)
+    int last_frames = 0;
+
+    // counters
+    uint64_t kernel_launches = 0, extend_launches = 0;
+    double build_ms = 0.0;
+    std::vector<cudaEvent_t> events;
+    std::vector<int> ev_tag;
+    int ev_used = 0;
+    double extend_ms_acc = 0.0, shade_ms_acc = 0.0;
+
+    ncclComm_t comm = nullptr;
+};
+
+namespace {
+
+int fail(rt_ctx* c, int code, const std::string& msg) {
+    if (c) {
+        c->err = msg;
+        if (code == RT_ERR_CUDA || code == RT_ERR_NCCL) c->sticky = code;
+    } else {
+        g_static_err = msg;
+    }
+    return code;
+}
+#define CK(expr)                                                                                    \
+    do {                                                                                            \
+        cudaError_t e__ = (expr);                                                                   \
+        if (e__ != cudaSuccess)                                                                     \
+            return fail(ctx, e__ == cudaErrorMemoryAllocation ? RT_ERR_OOM : RT_ERR_CUDA,           \
+                        std::string(#expr) + ": " + cudaGetErrorString(e__));                       \
+    } while (0)
+#define CKN(expr)                                                                                   \
+    do {                                                                                            \
+        ncclResult_t r__ = (expr);                                                                  \
+        if (r__ != 0)                                                                               \
+            return fail(ctx, RT_ERR_NCCL,                                                           \
+                        std::string(#expr) + ": " +                                                 \
+                            (nccl().GetErrorString ? nccl().GetErrorString(r__) : "nccl error"));   \
+    } while (0)
+#define GUARD()                                                                                     \
+    do {                                                                                            \
+        if (!ctx) return fail(nullptr, RT_ERR_INVALID, "ctx is NULL");                              \
+        if (ctx->sticky != RT_OK) return ctx->sticky;                                               \
+        cudaSetDevice(ctx->cfg.device);                                                             \
+    } while (0)
+
+Launcher make_launcher(rt_ctx* ctx) {
+    Launcher L;
+    L.st = ctx->stream;
+    L.sm_count = ctx->sm_count;
+    L.rng_mode = ctx->cfg.rng_mode;
+    L.instrument = ctx->cfg.instrument != 0;
+    L.kernel_launches = &ctx->kernel_launches;
+    L.extend_launches = &ctx->extend_launches;
+    L.ev_pool = ctx->events.data();
+    L.ev_cap = (int)ctx->events.size();
+    L.ev_used = &ctx->ev_used;
+    L.ev_tag = ctx->ev_tag.data();
+    L.timing = ctx->cfg.kernel_timing != 0 && !ctx->events.empty();
+    return L;
+}
+
+SceneView make_view(rt_ctx* ctx) {
+    SceneView v;
+    memset(&v, 0, sizeof v);
+    v.nodes = ctx->d_nodes.as<float4>();
+    v.tri_geom = ctx->d_geom.as<float4>();
+    v.tri_shade = ctx->d_shade.as<float4>();
+    v.tri_orig = ctx->d_orig.as<int32_t>();
+    v.materials = ctx->d_mats.as<float4>();
+    for (int i = 0; i < RT_MAX_TEXTURES; i++) {
+        v.tex_px[i] = ctx->d_tex[i].as<uint8_t>();
+        v.tex_w[i] = ctx->tex_w[i];
+        v.tex_h[i] = ctx->tex_h[i];
+        v.tex_ch[i] = ctx->tex_ch[i];
+    }
+    v.num_tris = (int32_t)ctx->n_tris;
+    v.num_materials = ctx->n_mats;
+    v.root_is_leaf = ctx->n_tris == 1 ? 1 : 0;
+    return v;
+}
+
+// drain the event pool into the accumulated per-class times (stream must be idle)
+void harvest_events(rt_ctx* ctx) {
+    for (int i = 0; i + 1 < ctx->ev_used; i += 2) {
+        float ms = 0.0f;
+        if (cudaEventElapsedTime(&ms, ctx->events[i], ctx->events[i + 1]) == cudaSuccess) {
+            if (ctx->ev_tag[i] == 0) ctx->extend_ms_acc += ms; else ctx->shade_ms_acc += ms;
+        }
+    }
+    ctx->ev_used = 0;
+}
+
+int validate_uniforms(rt_ctx* ctx, const rt_uniforms* u) {
+    if (!u) return fail(ctx, RT_ERR_INVALID, "uniforms is NULL");
+    if (u->width == 0 || u->height == 0 || u->width > 65536 || u->height > 65536)
+        return fail(ctx, RT_ERR_INVALID, "bad image size");
+    if (u->maxBounceCount > kMaxBounces) return fail(ctx, RT_ERR_INVALID, "maxBounceCount too large");
+    if (u->basicShading == 0 && u->numRaysPerPixel <= 0) return fail(ctx, RT_ERR_INVALID, "numRaysPerPixel must be > 0");
+    if (!ctx->built) return fail(ctx, RT_ERR_STATE, "scene not built: call rt_scene_build first");
+    return RT_OK;
+}
+
+// (re)allocate everything that depends on the image size and the split
+int prepare_image(rt_ctx* ctx, int W, int H) {
+    if (W == ctx->width && H == ctx->height && !ctx->rows.empty()) return RT_OK;
+    ctx->width = W;
+    ctx->height = H;
+    ctx->rows.clear();
+    if (ctx->cfg.split_mode == RT_SPLIT_TILES && ctx->cfg.world_size > 1) {
+        ctx->rows.resize((size_t)H);
+        const int64_t n = rt_split_rows(H, ctx->cfg.band_rows, ctx->cfg.rank, ctx->cfg.world_size, ctx->rows.data(), H);
+        ctx->rows.resize((size_t)n);
+    } else {
+        ctx->rows.resize((size_t)H);
+        for (int y = 0; y < H; y++) ctx->rows[(size_t)y] = y;
+    }
+    const size_t P = (size_t)W * ctx->rows.size();
+    CK(ctx->d_rows.reserve(std::max<size_t>(ctx->rows.size(), 1) * sizeof(int32_t)));
+    if (!ctx->rows.empty())
+        CK(cudaMemcpyAsync(ctx->d_rows.p, ctx->rows.data(), ctx->rows.size() * sizeof(int32_t), cudaMemcpyHostToDevice,
+                           ctx->stream));
+    CK(ctx->d_accum.reserve(std::max<size_t>(P, 1) * sizeof(float4)));
+    CK(ctx->d_pixrng.reserve(std::max<size_t>(P, 1) * sizeof(uint32_t)));
+    CK(ctx->d_image.reserve((size_t)W * H * sizeof(float4)));
+    CK(ctx->d_sum.reserve((size_t)W * H * 3 * sizeof(uint32_t)));
+    CK(ctx->d_out.reserve((size_t)W * H * 3));
+    CK(ctx->d_counts.reserve((size_t)(kMaxBounces + 2) * sizeof(uint32_t)));
+    CK(cudaMemsetAsync(ctx->d_image.p, 0, (size_t)W * H * sizeof(float4), ctx->stream));
+    return RT_OK;
+}
+
+int lanes_for(rt_ctx* ctx, size_t P, int spp) {
+    if (ctx->cfg.rng_mode == RT_RNG_REF_PCG) return 1;  // the reference stream is sequential per pixel
+    const uint64_t budget = ctx->cfg.max_paths_in_flight ? ctx->cfg.max_paths_in_flight : (uint64_t)16 << 20;
+    uint64_t lanes = P ? budget / P : 1;
+    if (lanes < 1) lanes = 1;
+    if (lanes > (uint64_t)spp) lanes = (uint64_t)spp;
+    return (int)lanes;
+}
+
+int prepare_paths(rt_ctx* ctx, size_t slots) {
+    slots = std::max<size_t>(slots, 1);
+    for (int i = 0; i < 6; i++) CK(ctx->d_path[i].reserve(slots * sizeof(float4)));
+    CK(ctx->d_hit.reserve(slots * sizeof(float4)));
+    CK(ctx->d_contrib.reserve(slots * sizeof(float4)));
+    return RT_OK;
+}
+
+WaveBuffers make_wave(rt_ctx* ctx) {
+    WaveBuffers wb;
+    wb.cur = PathArrays{ctx->d_path[0].as<float4>(), ctx->d_path[1].as<float4>(), ctx->d_path[2].as<float4>()};
+    wb.next = PathArrays{ctx->d_path[3].as<float4>(), ctx->d_path[4].as<float4>(), ctx->d_path[5].as<float4>()};
+    wb.hit = ctx->d_hit.as<float4>();
+    wb.contrib = ctx->d_contrib.as<float4>();
+    wb.accum = ctx->d_accum.as<float4>();
+    wb.pix_rng = ctx->d_pixrng.as<uint32_t>();
+    wb.counts = ctx->d_counts.as<uint32_t>();
+    wb.stats = ctx->d_stats.as<unsigned long long>();
+    wb.image = ctx->d_image.as<float4>();
+    wb.frame_sum = ctx->d_sum.as<uint32_t>();
+    wb.out_rgb8 = ctx->d_out.as<uint8_t>();
+    return wb;
+}
+
+FrameParams make_params(rt_ctx* ctx, const rt_uniforms& u) {
+    FrameParams fp;
+    memset(&fp, 0, sizeof fp);
+    fp.u = u;
+    fp.width = (int)u.width;
+    fp.height = (int)u.height;
+    fp.local_pixels = (int)((size_t)u.width * ctx->rows.size());
+    fp.rows = ctx->d_rows.as<int32_t>();
+    fp.lanes = 1;
+    fp.lanes_active = 1;
+    return fp;
+}
+
+// one frame = numRaysPerPixel samples per local pixel, left in `accum`, resolved into image (+sum)
+int render_one_frame(rt_ctx* ctx, const rt_uniforms& u, bool add_to_sum) {
+    const int W = (int)u.width, H = (int)u.height;
+    int rc = prepare_image(ctx, W, H);
+    if (rc) return rc;
+    Launcher L = make_launcher(ctx);
+    SceneView sc = make_view(ctx);
+    FrameParams fp = make_params(ctx, u);
+    if (fp.local_pixels == 0) return RT_OK;
+    if (u.basicShading != 0) {
+        WaveBuffers wb = make_wave(ctx);
+        CK(wf_preview(L, sc, wb, fp));
+        return RT_OK;
+    }
+    const int spp = u.numRaysPerPixel;
+    const int lanes = lanes_for(ctx, (size_t)fp.local_pixels, spp);
+    rc = prepare_paths(ctx, (size_t)fp.local_pixels * lanes);
+    if (rc) return rc;
+    WaveBuffers wb = make_wave(ctx);
+    fp.lanes = lanes;
+    CK(wf_clear_accum(L, wb, fp.local_pixels));
+    if (ctx->cfg.rng_mode == RT_RNG_REF_PCG) CK(wf_seed_pixels(L, sc, wb, fp));
+    for (int base = 0; base < spp; base += lanes) {
+        fp.sample_base = base;
+        fp.lanes_active = std::min(lanes, spp - base);
+        CK(wf_render_batch(L, sc, wb, fp));
+    }
+    CK(wf_resolve_frame(L, wb, fp, add_to_sum));
+    return RT_OK;
+}
+
+// partial sums of the frames (or rows) this rank owns, left in d_sum
+int render_partial(rt_ctx* ctx, const rt_uniforms* uniforms, int frames) {
+    int rc = validate_uniforms(ctx, uniforms);
+    if (rc) return rc;
+    if (frames <= 0) return fail(ctx, RT_ERR_INVALID, "frames must be > 0");
+    const int W = (int)uniforms->width, H = (int)uniforms->height;
+    rc = prepare_image(ctx, W, H);
+    if (rc) return rc;
+    CK(cudaMemsetAsync(ctx->d_sum.p, 0, (size_t)W * H * 3 * sizeof(uint32_t), ctx->stream));
+    const bool frameSplit = ctx->cfg.split_mode == RT_SPLIT_FRAMES && ctx->cfg.world_size > 1;
+    for (int f = 0; f < frames; f++) {
+        if (frameSplit && (f % ctx->cfg.world_size) != ctx->cfg.rank) continue;
+        rt_uniforms uf = *uniforms;
+        uf.frameIndex = (uint32_t)f;  // rayTracing.cpp:187
+        uf.basicShading = 0;          // rayTracing.cpp:146 (SCREENSHOT_BASIC_SHADING)
+        rc = render_one_frame(ctx, uf, true);
+        if (rc) return rc;
+        // keep the event pool from overflowing on long screenshots
+        if (ctx->cfg.kernel_timing && ctx->ev_used > kEventCap - 512) {
+            CK(cudaStreamSynchronize(ctx->stream));
+            harvest_events(ctx);
+        }
+    }
+    ctx->last_frames = frames;
+    return RT_OK;
+}
+
+// bring every rank's partial sums to rank 0 (d_sum of rank 0 holds the total afterwards)
+int exchange_partials(rt_ctx* ctx) {
+    if (ctx->cfg.world_size <= 1 || ctx->cfg.split_mode == RT_SPLIT_NONE) return RT_OK;
+    if (!ctx->comm) return fail(ctx, RT_ERR_STATE, "world_size > 1 but rt_comm_init was not called");
+    NcclApi& N = nccl();
+    const int W = ctx->width, H = ctx->height;
+    const size_t count = (size_t)W * H * 3;
+    if (ctx->cfg.split_mode == RT_SPLIT_FRAMES) {
+        // sums of 8-bit integers: exact in u32, so the total is independent of the GPU count
+        CKN(N.Reduce(ctx->d_sum.p, ctx->d_sum.p, count, ncclUint32, ncclSum, 0, ctx->comm, ctx->stream));
+        return RT_OK;
+    }
+    // RT_SPLIT_TILES: a gather, not a reduce — each rank ships only the rows it rendered
+    Launcher L = make_launcher(ctx);
+    const size_t rowLen = (size_t)W * 3;
+    if (ctx->cfg.rank != 0) {
+        CK(ctx->d_compact.reserve(std::max<size_t>(ctx->rows.size() * rowLen, 1) * sizeof(uint32_t)));
+        CK(wf_gather_rows(L, ctx->d_sum.as<uint32_t>(), ctx->d_compact.as<uint32_t>(), ctx->d_rows.as<int32_t>(),
+                          (int)ctx->rows.size(), W));
+        if (!ctx->rows.empty())
+            CKN(N.Send(ctx->d_compact.p, ctx->rows.size() * rowLen, ncclUint32, 0, ctx->comm, ctx->stream));
+        return RT_OK;
+    }
+    std::vector<std::vector<int32_t>> peerRows((size_t)ctx->cfg.world_size);
+    size_t total = 0;
+    for (int r = 1; r < ctx->cfg.world_size; r++) {
+        peerRows[(size_t)r].resize((size_t)H);
+        const int64_t n = rt_split_rows(H, ctx->cfg.band_rows, r, ctx->cfg.world_size, peerRows[(size_t)r].data(), H);
+        peerRows[(size_t)r].resize((size_t)n);
+        total += (size_t)n;
+    }
+    CK(ctx->d_stage.reserve(std::max<size_t>(total * rowLen, 1) * sizeof(uint32_t)));
+    CK(ctx->d_compact.reserve(std::max<size_t>(total, 1) * sizeof(int32_t)));
+    std::vector<int32_t> allRows;
+    for (int r = 1; r < ctx->cfg.world_size; r++) allRows.insert(allRows.end(), peerRows[(size_t)r].begin(), peerRows[(size_t)r].end());
+    if (total) CK(cudaMemcpyAsync(ctx->d_compact.p, allRows.data(), total * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->stream));
+    CKN(N.GroupStart());
+    size_t off = 0;
+    for (int r = 1; r < ctx->cfg.world_size; r++) {
+        const size_t n = peerRows[(size_t)r].size();
+        if (n) CKN(N.Recv(ctx->d_stage.as<uint32_t>() + off * rowLen, n * rowLen, ncclUint32, r, ctx->comm, ctx->stream));
+        off += n;
+    }
+    CKN(N.GroupEnd());
+    CK(wf_scatter_rows(L, ctx->d_stage.as<uint32_t>(), ctx->d_sum.as<uint32_t>(), ctx->d_compact.as<int32_t>(), (int)total, W));
+    CK(cudaStreamSynchronize(ctx->stream));  // allRows must outlive the async copy
+    return RT_OK;
+}
+
+}  // namespace
+
+// ================================================================================================
+extern "C" {
+
+const char* rt_version(void) { return "rt_b200 0.1 (sm_100a)"; }
+
+const char* rt_last_error(const rt_ctx* ctx) { return ctx ? ctx->err.c_str() : g_static_err.c_str(); }
+
+int rt_create(rt_ctx** out, const rt_config* cfg) {
+    if (!out || !cfg) return fail(nullptr, RT_ERR_INVALID, "rt_create: NULL argument");
+    *out = nullptr;
+    if (cfg->world_size < 1 || cfg->rank < 0 || cfg->rank >= cfg->world_size)
+        return fail(nullptr, RT_ERR_INVALID, "rt_create: bad rank / world_size");
+    if (cfg->rng_mode != RT_RNG_REF_PCG && cfg->rng_mode != RT_RNG_PHILOX)
+        return fail(nullptr, RT_ERR_INVALID, "rt_create: bad rng_mode");
+    if (cfg->split_mode < RT_SPLIT_NONE || cfg->split_mode > RT_SPLIT_FRAMES)
+        return fail(nullptr, RT_ERR_INVALID, "rt_create: bad split_mode");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev <= 0)
+        return fail(nullptr, RT_ERR_NO_DEVICE,
+                    std::string("rt_create: no CUDA device (this backend has no CPU fallback): ") + cudaGetErrorString(e));
+    if (cfg->device < 0 || cfg->device >= ndev) return fail(nullptr, RT_ERR_INVALID, "rt_create: bad device ordinal");
+    rt_ctx* ctx = new (std::nothrow) rt_ctx;
+    if (!ctx) return fail(nullptr, RT_ERR_OOM, "rt_create: out of host memory");
+    ctx->cfg = *cfg;
+    cudaSetDevice(cfg->device);
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, cfg->device) == cudaSuccess) ctx->sm_count = prop.multiProcessorCount;
+    e = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) {
+        std::string m = std::string("rt_create: cudaStreamCreate: ") + cudaGetErrorString(e);
+        delete ctx;
+        return fail(nullptr, RT_ERR_CUDA, m);
+    }
+    ctx->stream = ctx->own_stream;
+    if (ctx->d_stats.reserve(4 * sizeof(unsigned long long)) != cudaSuccess ||
+        cudaMemsetAsync(ctx->d_stats.p, 0, 4 * sizeof(unsigned long long), ctx->stream) != cudaSuccess) {
+        delete ctx;
+        return fail(nullptr, RT_ERR_CUDA, "rt_create: cannot allocate counters");
+    }
+    if (cfg->kernel_timing) {
+        ctx->events.resize(kEventCap);
+        ctx->ev_tag.resize(kEventCap);
+        for (auto& ev : ctx->events) cudaEventCreate(&ev);
+    }
+    *out = ctx;
+    return RT_OK;
+}
+
+void rt_destroy(rt_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->cfg.device);
+    cudaStreamSynchronize(ctx->stream);
+    if (ctx->comm && nccl().ok) nccl().CommDestroy(ctx->comm);
+    DevBuf* all[] = {&ctx->d_tris, &ctx->d_mats, &ctx->d_centroid, &ctx->d_bounds, &ctx->d_keys[0], &ctx->d_keys[1],
+                     &ctx->d_vals[0], &ctx->d_vals[1], &ctx->d_hist, &ctx->d_children, &ctx->d_parent, &ctx->d_boxes,
+                     &ctx->d_flags, &ctx->d_depth, &ctx->d_nodes, &ctx->d_geom, &ctx->d_shade, &ctx->d_orig, &ctx->d_hit,
+                     &ctx->d_contrib, &ctx->d_accum, &ctx->d_pixrng, &ctx->d_counts, &ctx->d_stats, &ctx->d_image,
+                     &ctx->d_sum, &ctx->d_out, &ctx->d_rows, &ctx->d_stage, &ctx->d_compact};
+    for (DevBuf* b : all) b->release();
+    for (auto& b : ctx->d_tex) b.release();
+    for (auto& b : ctx->d_path) b.release();
+    for (auto& b : ctx->d_scratch) b.release();
+    for (auto& ev : ctx->events) cudaEventDestroy(ev);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+    delete ctx;
+}
+
+int rt_set_stream(rt_ctx* ctx, void* cuda_stream) {
+    GUARD();
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
+    return RT_OK;
+}
+
+int rt_scene_set_triangles(rt_ctx* ctx, const rt_triangle* tris, int64_t count) {
+    GUARD();
+    if (count < 0 || (count > 0 && !tris)) return fail(ctx, RT_ERR_INVALID, "rt_scene_set_triangles: bad argument");
+    if (count > (int64_t)kLeafFirstMask) return fail(ctx, RT_ERR_INVALID, "rt_scene_set_triangles: more than 2^27-1 triangles");
+    CK(ctx->d_tris.reserve(std::max<size_t>((size_t)count, 1) * sizeof(rt_triangle)));
+    if (count) CK(cudaMemcpyAsync(ctx->d_tris.p, tris, (size_t)count * sizeof(rt_triangle), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));  // glBufferData semantics: the caller may free at once
+    ctx->n_tris = count;
+    ctx->built = false;
+    // material indices are validated on the host copy the caller still owns
+    int32_t maxMat = -1, minMat = 0;
+    for (int64_t i = 0; i < count; i++) {
+        maxMat = std::max(maxMat, tris[i].materialIndex);
+        minMat = std::min(minMat, tris[i].materialIndex);
+    }
+    if (minMat < 0) return fail(ctx, RT_ERR_INVALID, "rt_scene_set_triangles: negative materialIndex");
+    ctx->max_mat_index = maxMat;
+    return RT_OK;
+}
+
+int rt_scene_set_materials(rt_ctx* ctx, const rt_material* mats, int32_t count) {
+    GUARD();
+    if (count <= 0 || !mats) return fail(ctx, RT_ERR_INVALID, "rt_scene_set_materials: bad argument");
+    CK(ctx->d_mats.reserve((size_t)count * sizeof(rt_material)));
+    CK(cudaMemcpyAsync(ctx->d_mats.p, mats, (size_t)count * sizeof(rt_material), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->n_mats = count;
+    return RT_OK;
+}
+
+int rt_scene_set_texture(rt_ctx* ctx, int32_t slot, const uint8_t* pixels, int32_t w, int32_t h, int32_t ch) {
+    GUARD();
+    if (slot < 0 || slot >= RT_MAX_TEXTURES || !pixels || w <= 0 || h <= 0 || ch < 1 || ch > 4)
+        return fail(ctx, RT_ERR_INVALID, "rt_scene_set_texture: bad argument");
+    const size_t bytes = (size_t)w * h * ch;
+    CK(ctx->d_tex[slot].reserve(bytes));
+    CK(cudaMemcpyAsync(ctx->d_tex[slot].p, pixels, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->tex_w[slot] = w;
+    ctx->tex_h[slot] = h;
+    ctx->tex_ch[slot] = ch;
+    return RT_OK;
+}
+
+int rt_scene_build(rt_ctx* ctx) {
+    GUARD();
+    if (ctx->n_mats <= 0) return fail(ctx, RT_ERR_STATE, "rt_scene_build: no materials");
+    if (ctx->n_tris > 0 && ctx->max_mat_index >= ctx->n_mats)
+        return fail(ctx, RT_ERR_INVALID, "rt_scene_build: a triangle's materialIndex is out of range");
+    const int n = (int)ctx->n_tris;
+    ctx->built = false;
+    if (n == 0) {
+        ctx->built = true;
+        ctx->bvh_depth = 0;
+        return RT_OK;
+    }
+    const size_t nn = (size_t)std::max(n - 1, 1);
+    CK(ctx->d_centroid.reserve((size_t)n * sizeof(float4)));
+    CK(ctx->d_bounds.reserve(12 * sizeof(uint32_t)));
+    for (int i = 0; i < 2; i++) {
+        CK(ctx->d_keys[i].reserve((size_t)n * sizeof(uint64_t)));
+        CK(ctx->d_vals[i].reserve((size_t)n * sizeof(uint32_t)));
+    }
+    CK(ctx->d_hist.reserve(sort_hist_entries(n) * sizeof(uint32_t)));
+    CK(ctx->d_children.reserve(2 * nn * sizeof(int32_t)));
+    CK(ctx->d_parent.reserve((size_t)(2 * n) * sizeof(int32_t)));
+    CK(ctx->d_boxes.reserve((size_t)(2 * n) * 2 * sizeof(float4)));
+    CK(ctx->d_flags.reserve(nn * sizeof(uint32_t)));
+    CK(ctx->d_depth.reserve(sizeof(uint32_t)));
+    CK(ctx->d_nodes.reserve(nn * 4 * sizeof(float4)));
+    CK(ctx->d_geom.reserve((size_t)n * 3 * sizeof(float4)));
+    CK(ctx->d_shade.reserve((size_t)n * 2 * sizeof(float4)));
+    CK(ctx->d_orig.reserve((size_t)n * sizeof(int32_t)));
+    BuildArgs a;
+    a.tris = ctx->d_tris.as<rt_triangle>();
+    a.n = n;
+    a.centroid = ctx->d_centroid.as<float4>();
+    a.bounds = ctx->d_bounds.as<uint32_t>();
+    for (int i = 0; i < 2; i++) {
+        a.keys[i] = ctx->d_keys[i].as<uint64_t>();
+        a.vals[i] = ctx->d_vals[i].as<uint32_t>();
+    }
+    a.hist = ctx->d_hist.as<uint32_t>();
+    a.children = ctx->d_children.as<int32_t>();
+    a.parent = ctx->d_parent.as<int32_t>();
+    a.boxes = ctx->d_boxes.as<float4>();
+    a.flags = ctx->d_flags.as<uint32_t>();
+    a.maxDepth = ctx->d_depth.as<uint32_t>();
+    a.nodes = ctx->d_nodes.as<float4>();
+    a.geom = ctx->d_geom.as<float4>();
+    a.shade = ctx->d_shade.as<float4>();
+    a.orig = ctx->d_orig.as<int32_t>();
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0));
+    CK(cudaEventCreate(&e1));
+    CK(cudaEventRecord(e0, ctx->stream));
+    CK(build_lbvh(a, ctx->stream, &ctx->kernel_launches));
+    CK(cudaEventRecord(e1, ctx->stream));
+    uint32_t depth = 0;
+    CK(cudaMemcpyAsync(&depth, ctx->d_depth.p, sizeof depth, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    float ms = 0.0f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    ctx->build_ms = ms;
+    ctx->bvh_depth = depth;
+    if ((int)depth + 1 >= kStackSize)
+        return fail(ctx, RT_ERR_INVALID, "rt_scene_build: BVH deeper than the traversal stack (" + std::to_string(depth) + ")");
+    ctx->built = true;
+    return RT_OK;
+}
+
+int rt_render_frame(rt_ctx* ctx, const rt_uniforms* uniforms) {
+    GUARD();
+    int rc = validate_uniforms(ctx, uniforms);
+    if (rc) return rc;
+    return render_one_frame(ctx, *uniforms, false);
+}
+
+int rt_read_frame_rgba32f(rt_ctx* ctx, float* dst) {
+    GUARD();
+    if (!dst || ctx->width == 0) return fail(ctx, RT_ERR_INVALID, "rt_read_frame_rgba32f: nothing rendered / NULL dst");
+    CK(cudaMemcpyAsync(dst, ctx->d_image.p, (size_t)ctx->width * ctx->height * sizeof(float4), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return RT_OK;
+}
+
+int rt_screenshot_partial(rt_ctx* ctx, const rt_uniforms* uniforms, int32_t frames) {
+    GUARD();
+    return render_partial(ctx, uniforms, frames);
+}
+
+int rt_read_frame_sum(rt_ctx* ctx, uint32_t* dst) {
+    GUARD();
+    if (!dst || ctx->width == 0) return fail(ctx, RT_ERR_INVALID, "rt_read_frame_sum: nothing rendered / NULL dst");
+    CK(cudaMemcpyAsync(dst, ctx->d_sum.p, (size_t)ctx->width * ctx->height * 3 * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return RT_OK;
+}
+
+int rt_finalize_sums(rt_ctx* ctx, const uint32_t* sums, int32_t width, int32_t height, int32_t frames, uint8_t* rgb8) {
+    GUARD();
+    if (!sums || !rgb8 || width <= 0 || height <= 0 || frames <= 0) return fail(ctx, RT_ERR_INVALID, "rt_finalize_sums: bad argument");
+    const size_t count = (size_t)width * height * 3;
+    CK(ctx->d_scratch[0].reserve(count * sizeof(uint32_t)));
+    CK(ctx->d_scratch[1].reserve(count));
+    CK(cudaMemcpyAsync(ctx->d_scratch[0].p, sums, count * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+    Launcher L = make_launcher(ctx);
+    CK(wf_finalize(L, ctx->d_scratch[0].as<uint32_t>(), ctx->d_scratch[1].as<uint8_t>(), width, height, frames));
+    CK(cudaMemcpyAsync(rgb8, ctx->d_scratch[1].p, count, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return RT_OK;
+}
+
+int rt_screenshot_device(rt_ctx* ctx, const rt_uniforms* uniforms, int32_t frames) {
+    GUARD();
+    int rc = render_partial(ctx, uniforms, frames);
+    if (rc) return rc;
+    rc = exchange_partials(ctx);
+    if (rc) return rc;
+    if (ctx->cfg.rank == 0) {
+        Launcher L = make_launcher(ctx);
+        CK(wf_finalize(L, ctx->d_sum.as<uint32_t>(), ctx->d_out.as<uint8_t>(), ctx->width, ctx->height, frames));
+    }
+    return RT_OK;
+}
+
+int rt_screenshot_fetch(rt_ctx* ctx, uint8_t* rgb8) {
+    GUARD();
+    if (ctx->width == 0) return fail(ctx, RT_ERR_STATE, "rt_screenshot_fetch: nothing rendered");
+    if (ctx->cfg.rank == 0) {
+        if (!rgb8) return fail(ctx, RT_ERR_INVALID, "rt_screenshot_fetch: NULL destination on rank 0");
+        CK(cudaMemcpyAsync(rgb8, ctx->d_out.p, (size_t)ctx->width * ctx->height * 3, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    CK(cudaStreamSynchronize(ctx->stream));
+    return RT_OK;
+}
+
+int rt_screenshot(rt_ctx* ctx, const rt_uniforms* uniforms, int32_t frames, uint8_t* rgb8) {
+    int rc = rt_screenshot_device(ctx, uniforms, frames);
+    if (rc) return rc;
+    return rt_screenshot_fetch(ctx, rgb8);
+}
+
+int rt_first_hit(rt_ctx* ctx, const rt_uniforms* uniforms, int32_t mode, int32_t* tri_id, float* dst) {
+    GUARD();
+    int rc = validate_uniforms(ctx, uniforms);
+    if (rc) return rc;
+    if (mode != RT_FIRST_HIT_CENTRE && mode != RT_FIRST_HIT_SAMPLE0) return fail(ctx, RT_ERR_INVALID, "rt_first_hit: bad mode");
+    const size_t n = (size_t)uniforms->width * uniforms->height;
+    CK(ctx->d_scratch[0].reserve(n * sizeof(int32_t)));
+    CK(ctx->d_scratch[1].reserve(n * sizeof(float)));
+    Launcher L = make_launcher(ctx);
+    SceneView sc = make_view(ctx);
+    FrameParams fp;
+    memset(&fp, 0, sizeof fp);
+    fp.u = *uniforms;
+    fp.width = (int)uniforms->width;
+    fp.height = (int)uniforms->height;
+    CK(wf_first_hit(L, sc, fp, mode, ctx->d_scratch[0].as<int32_t>(), ctx->d_scratch[1].as<float>()));
+    if (tri_id) CK(cudaMemcpyAsync(tri_id, ctx->d_scratch[0].p, n * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    if (dst) CK(cudaMemcpyAsync(dst, ctx->d_scratch[1].p, n * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return RT_OK;
+}
+
+int rt_trace_rays(rt_ctx* ctx, const float* origins, const float* dirs, int64_t count, int32_t* tri_id, float* dst,
+                  float* bu, float* bv) {
+    GUARD();
+    if (!ctx->built) return fail(ctx, RT_ERR_STATE, "scene not built: call rt_scene_build first");
+    if (count < 0 || (count > 0 && (!origins || !dirs))) return fail(ctx, RT_ERR_INVALID, "rt_trace_rays: bad argument");
+    if (count == 0) return RT_OK;
+    const size_t n = (size_t)count;
+    CK(ctx->d_scratch[0].reserve(n * 3 * sizeof(float)));
+    CK(ctx->d_scratch[1].reserve(n * 3 * sizeof(float)));
+    for (int i = 2; i < 6; i++) CK(ctx->d_scratch[i].reserve(n * sizeof(float)));
+    CK(cudaMemcpyAsync(ctx->d_scratch[0].p, origins, n * 3 * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->d_scratch[1].p, dirs, n * 3 * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    Launcher L = make_launcher(ctx);
+    SceneView sc = make_view(ctx);
+    CK(wf_trace_rays(L, sc, ctx->d_scratch[0].as<float>(), ctx->d_scratch[1].as<float>(), count,
+                     ctx->d_scratch[2].as<int32_t>(), ctx->d_scratch[3].as<float>(), ctx->d_scratch[4].as<float>(),
+                     ctx->d_scratch[5].as<float>(), ctx->d_stats.as<unsigned long long>()));
+    if (tri_id) CK(cudaMemcpyAsync(tri_id, ctx->d_scratch[2].p, n * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    if (dst) CK(cudaMemcpyAsync(dst, ctx->d_scratch[3].p, n * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    if (bu) CK(cudaMemcpyAsync(bu, ctx->d_scratch[4].p, n * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    if (bv) CK(cudaMemcpyAsync(bv, ctx->d_scratch[5].p, n * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return RT_OK;
+}
+
+int rt_scene_get_bvh(rt_ctx* ctx, rt_bvh_node* nodes, int64_t* node_count, int32_t* sorted_tri_ids, int64_t* tri_count,
+                     float scene_lo[3], float scene_hi[3]) {
+    GUARD();
+    if (!ctx->built) return fail(ctx, RT_ERR_STATE, "scene not built");
+    const int64_t n = ctx->n_tris;
+    const int64_t nn = n >= 2 ? n - 1 : 0;
+    if (node_count) *node_count = nn;
+    if (tri_count) *tri_count = n;
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (nodes && nn > 0) {
+        std::vector<float4> raw((size_t)nn * 4);
+        CK(cudaMemcpy(raw.data(), ctx->d_nodes.p, raw.size() * sizeof(float4), cudaMemcpyDeviceToHost));
+        for (int64_t i = 0; i < nn; i++) {
+            const float4 n0 = raw[(size_t)i * 4], n1 = raw[(size_t)i * 4 + 1], n2 = raw[(size_t)i * 4 + 2], n3 = raw[(size_t)i * 4 + 3];
+            rt_bvh_node& o = nodes[i];
+            o.lo_x[0] = n0.x; o.hi_x[0] = n0.y; o.lo_y[0] = n0.z; o.hi_y[0] = n0.w;
+            o.lo_x[1] = n1.x; o.hi_x[1] = n1.y; o.lo_y[1] = n1.z; o.hi_y[1] = n1.w;
+            o.lo_z[0] = n2.x; o.hi_z[0] = n2.y; o.lo_z[1] = n2.z; o.hi_z[1] = n2.w;
+            int32_t c[2];
+            memcpy(&c[0], &n3.x, 4);
+            memcpy(&c[1], &n3.y, 4);
+            for (int k = 0; k < 2; k++) {
+                if (c[k] >= 0) {
+                    o.child[k] = c[k];
+                    o.count[k] = 0;
+                } else {
+                    const int32_t packed = ~c[k];
+                    o.child[k] = ~(packed & kLeafFirstMask);
+                    o.count[k] = (packed >> kLeafCountShift) + 1;
+                }
+            }
+        }
+    }
+    if (sorted_tri_ids && n > 0) CK(cudaMemcpy(sorted_tri_ids, ctx->d_orig.p, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToHost));
+    if ((scene_lo || scene_hi) && n > 0) {
+        uint32_t b[12];
+        CK(cudaMemcpy(b, ctx->d_bounds.p, sizeof b, cudaMemcpyDeviceToHost));
+        auto ord2f = [](uint32_t u) {
+            u = (u & 0x80000000u) ? (u & 0x7fffffffu) : ~u;
+            float f;
+            memcpy(&f, &u, 4);
+            return f;
+        };
+        for (int k = 0; k < 3; k++) {
+            if (scene_lo) scene_lo[k] = ord2f(b[6 + k]);
+            if (scene_hi) scene_hi[k] = ord2f(b[9 + k]);
+        }
+    }
+    return RT_OK;
+}
+
+int rt_get_counters(rt_ctx* ctx, rt_counters* out) {
+    GUARD();
+    if (!out) return fail(ctx, RT_ERR_INVALID, "rt_get_counters: NULL");
+    CK(cudaStreamSynchronize(ctx->stream));
+    harvest_events(ctx);
+    unsigned long long s[4];
+    CK(cudaMemcpy(s, ctx->d_stats.p, sizeof s, cudaMemcpyDeviceToHost));
+    memset(out, 0, sizeof *out);
+    out->segments = s[0];
+    out->paths = s[1];
+    out->node_visits = s[2];
+    out->tri_tests = s[3];
+    out->extend_launches = ctx->extend_launches;
+    out->kernel_launches = ctx->kernel_launches;
+    out->extend_ms = ctx->extend_ms_acc;
+    out->shade_ms = ctx->shade_ms_acc;
+    out->build_ms = ctx->build_ms;
+    out->bvh_nodes = ctx->n_tris >= 2 ? (uint64_t)ctx->n_tris - 1 : 0;
+    out->bvh_bytes = out->bvh_nodes * 64 + (uint64_t)ctx->n_tris * 48;
+    out->bvh_depth = ctx->bvh_depth;
+    return RT_OK;
+}
+
+int rt_reset_counters(rt_ctx* ctx) {
+    GUARD();
+    CK(cudaStreamSynchronize(ctx->stream));
+    harvest_events(ctx);
+    CK(cudaMemset(ctx->d_stats.p, 0, 4 * sizeof(unsigned long long)));
+    ctx->kernel_launches = 0;
+    ctx->extend_launches = 0;
+    ctx->extend_ms_acc = 0.0;
+    ctx->shade_ms_acc = 0.0;
+    return RT_OK;
+}
+
+int rt_comm_unique_id(uint8_t id_out[128]) {
+    if (!id_out) return fail(nullptr, RT_ERR_INVALID, "rt_comm_unique_id: NULL");
+    NcclApi& N = nccl();
+    if (!N.ok) return fail(nullptr, RT_ERR_NCCL, N.err);
+    ncclUniqueId id;
+    ncclResult_t r = N.GetUniqueId(&id);
+    if (r != 0) return fail(nullptr, RT_ERR_NCCL, "ncclGetUniqueId failed");
+    memcpy(id_out, id.internal, 128);
+    return RT_OK;
+}
+
+int rt_comm_init(rt_ctx* ctx, const uint8_t id[128]) {
+    GUARD();
+    if (!id) return fail(ctx, RT_ERR_INVALID, "rt_comm_init: NULL id");
+    NcclApi& N = nccl();
+    if (!N.ok) return fail(ctx, RT_ERR_NCCL, N.err);
+    if (ctx->comm) return fail(ctx, RT_ERR_STATE, "rt_comm_init: already initialised");
+    ncclUniqueId uid;
+    memcpy(uid.internal, id, 128);
+    CKN(N.CommInitRank(&ctx->comm, ctx->cfg.world_size, uid, ctx->cfg.rank));
+    return RT_OK;
+}
+
+int64_t rt_split_rows(int32_t height, int32_t band_rows, int32_t rank, int32_t world, int32_t* rows_out, int64_t cap) {
+    if (height <= 0 || world <= 0 || rank < 0 || rank >= world) return 0;
+    const int band = band_rows > 0 ? band_rows : 8;
+    int64_t n = 0;
+    for (int y = 0; y < height; y++) {
+        if (((y / band) % world) != rank) continue;
+        if (rows_out && n < cap) rows_out[n] = y;
+        n++;
+    }
+    return n;
+}
+
+int64_t rt_split_frames(int32_t frames, int32_t rank, int32_t world, int32_t* frames_out, int64_t cap) {
+    if (frames <= 0 || world <= 0 || rank < 0 || rank >= world) return 0;
+    int64_t n = 0;
+    for (int f = 0; f < frames; f++) {
+        if ((f % world) != rank) continue;
+        if (frames_out && n < cap) frames_out[n] = f;
+        n++;
+    }
+    return n;
+}
+
+}  // extern "C"

@@ -1,0 +1,93 @@
+// rt_internal.h — declarations shared by the translation units of librt_b200.so (not installed).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/rt_b200.h"
+#include "rt_scene.cuh"
+
+namespace rt {
+
+// ---------------------------------------------------------------- bvh_build.cu
+struct BuildArgs {
+    const rt_triangle* tris;  // device copy of the caller's array (original order)
+    int n;
+    float4* centroid;         // n
+    uint32_t* bounds;         // 12 order-preserving uints
+    uint64_t* keys[2];        // n each
+    uint32_t* vals[2];        // n each
+    uint32_t* hist;           // sort_hist_entries(n)
+    int32_t* children;        // 2*(n-1)
+    int32_t* parent;          // 2n-1
+    float4* boxes;            // 2*(2n-1)
+    uint32_t* flags;          // n-1
+    uint32_t* maxDepth;       // 1
+    float4* nodes;            // 4*(n-1)   (output)
+    float4* geom;             // 3*n       (output)
+    float4* shade;            // 2*n       (output)
+    int32_t* orig;            // n         (output)
+};
+cudaError_t build_lbvh(const BuildArgs& a, cudaStream_t st, uint64_t* launches);
+size_t sort_hist_entries(int n);
+
+// ---------------------------------------------------------------- wavefront.cu
+// Path state of the wavefront, structure of arrays, 16-byte records, ping-ponged between bounces
+// so that every kernel reads and writes dense, coalesced arrays.
+struct PathArrays {
+    float4* od0;   // origin.xyz, dir.x
+    float4* od1;   // dir.yz, throughput.xy
+    float4* misc;  // throughput.z, slot id (bits), rng carry (bits), flags (bits: bounce | insideGlass<<16)
+};
+struct FrameParams {
+    rt_uniforms u;
+    int32_t width, height;
+    int32_t local_pixels;       // pixels this rank renders
+    int32_t lanes;              // samples of a pixel in flight together (1 in RT_RNG_REF_PCG mode)
+    int32_t sample_base;        // first sample index of this batch
+    int32_t lanes_active;       // lanes of this batch that hold a real sample
+    const int32_t* rows;        // local row -> absolute row (RT_SPLIT_TILES), NULL = identity
+};
+struct WaveBuffers {
+    PathArrays cur, next;
+    float4* hit;          // t, u, v, slot(bits) per path of `cur`
+    float4* contrib;      // radiance of each (lane, pixel) slot of the batch
+    float4* accum;        // running sum per local pixel (xyz) 
+    uint32_t* pix_rng;    // RT_RNG_REF_PCG: the per-pixel stream state carried across samples
+    uint32_t* counts;     // counts[b] = live paths entering bounce b   (maxBounce + 2 entries)
+    unsigned long long* stats;  // [0] segments [1] paths [2] node visits [3] tri tests
+    float4* image;        // W*H RGBA32F, bottom-up (the reference's image binding 0)
+    uint32_t* frame_sum;  // W*H*3 sums of the 8-bit frames, bottom-up
+    uint8_t* out_rgb8;    // W*H*3 final, top-down
+};
+
+struct Launcher {
+    cudaStream_t st;
+    int sm_count;
+    int rng_mode;
+    bool instrument;
+    uint64_t* kernel_launches;
+    uint64_t* extend_launches;
+    // optional per-class device timing
+    cudaEvent_t* ev_pool;
+    int ev_cap;
+    int* ev_used;
+    int* ev_tag;  // 0 extend, 1 other
+    bool timing;
+};
+
+cudaError_t wf_clear_accum(const Launcher& L, const WaveBuffers& wb, int local_pixels);
+cudaError_t wf_seed_pixels(const Launcher& L, const SceneView& sc, const WaveBuffers& wb, const FrameParams& fp);
+cudaError_t wf_render_batch(const Launcher& L, const SceneView& sc, const WaveBuffers& wb, const FrameParams& fp);
+cudaError_t wf_resolve_frame(const Launcher& L, const WaveBuffers& wb, const FrameParams& fp, bool add_to_sum);
+cudaError_t wf_preview(const Launcher& L, const SceneView& sc, const WaveBuffers& wb, const FrameParams& fp);
+cudaError_t wf_finalize(const Launcher& L, const uint32_t* frame_sum, uint8_t* out, int w, int h, int frames);
+cudaError_t wf_first_hit(const Launcher& L, const SceneView& sc, const FrameParams& fp, int mode,
+                         int32_t* tri_id, float* dst);
+cudaError_t wf_trace_rays(const Launcher& L, const SceneView& sc, const float* o, const float* d, int64_t n,
+                          int32_t* tri, float* dst, float* bu, float* bv, unsigned long long* stats);
+cudaError_t wf_scatter_rows(const Launcher& L, const uint32_t* compact, uint32_t* full, const int32_t* rows,
+                            int nrows, int width);
+cudaError_t wf_gather_rows(const Launcher& L, const uint32_t* full, uint32_t* compact, const int32_t* rows,
+                           int nrows, int width);
+
+}  // namespace rt

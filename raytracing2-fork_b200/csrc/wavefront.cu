@@ -1,0 +1,729 @@
+// wavefront.cu — the per-pixel hot path as wavefront kernels (replaces the megakernel
+// RayTracing/Assets/Shaders/compute.glsl; citations S:line refer to that file, R:line to
+// RayTracing/src/rayTracing.cpp).
+//
+//   k_seed_pixels   S:668       per-pixel seed of the reference's sequential stream (PCG mode)
+//   k_raygen        S:660-690   NDC of the pixel corner, defocus arc, +-1/4 pixel jitter, first ray
+//   k_extend        S:410-460   closest hit of every live path (BVH2 traversal, rt_scene.cuh)
+//   k_shade         S:472-563   one bounce: material switch, next ray, Russian roulette; survivors
+//                               are compacted into the next queue with warp ballot + prefix popcount
+//   k_accumulate    S:692       per-pixel sum of the batch's samples, in sample order
+//   k_resolve       S:696-700   mean, ACES, gamma, image store; + unorm8 quantise and add (R:194-238)
+//   k_finalize      R:248-259   average of the 8-bit frames, truncate, flip
+//   k_preview       S:565-645   traceBasic, one thread per pixel (interactive preview)
+//   k_first_hit / k_trace_rays  parity hooks
+//
+// A "path slot" is (lane, pixel): `lanes` samples of every pixel are in flight together and each
+// slot owns one float4 of `contrib`; the radiance of a path is a single value written at its
+// terminal event (light hit / miss / error colour), so k_accumulate can add the lanes in sample
+// order and the image does not depend on the order in which paths finish.
+#include "rt_internal.h"
+
+namespace rt {
+
+constexpr int kBlock = 256;
+
+struct Material {
+    V3 color, emission;
+    int32_t textureIndex;
+    float emissionStrength, smoothness, specularProbability, checkerScale, refractiveIndex;
+    int32_t type, isEdgeHighlight;
+};
+__device__ __forceinline__ Material load_material(const SceneView& sc, int32_t idx) {
+    const float4 m0 = __ldg(&sc.materials[6 * idx + 0]);
+    const float4 m2 = __ldg(&sc.materials[6 * idx + 2]);
+    const float4 m3 = __ldg(&sc.materials[6 * idx + 3]);
+    const float4 m4 = __ldg(&sc.materials[6 * idx + 4]);
+    const float4 m5 = __ldg(&sc.materials[6 * idx + 5]);
+    Material m;
+    m.color = v3(m0);
+    m.emission = v3(m2);
+    m.textureIndex = __float_as_int(m3.x);
+    m.emissionStrength = m3.y;
+    m.smoothness = m3.z;
+    m.specularProbability = m3.w;
+    m.checkerScale = m4.x;
+    m.refractiveIndex = m4.y;
+    m.type = __float_as_int(m4.z);
+    m.isEdgeHighlight = __float_as_int(m5.x);
+    return m;
+}
+
+// GL_LINEAR / GL_REPEAT / unorm8, no mips (external/OpenGL/textureClass.cpp:95-101); DESIGN.md §4.6
+__device__ __forceinline__ V3 texel(const uint8_t* __restrict__ px, int w, int ch, int i, int j) {
+    const uint8_t* p = px + ((size_t)j * w + i) * ch;
+    const float r = (float)__ldg(p) / 255.0f;
+    if (ch == 1) return v3(r, r, r);
+    const float g = (float)__ldg(p + 1) / 255.0f;
+    if (ch == 2) return v3(r, g, 0.0f);
+    return v3(r, g, (float)__ldg(p + 2) / 255.0f);
+}
+__device__ __forceinline__ V3 sample_texture(const SceneView& sc, int t, float u, float v) {
+    const int w = sc.tex_w[t], h = sc.tex_h[t], ch = sc.tex_ch[t];
+    if (w <= 0 || h <= 0) return v3(0.0f, 0.0f, 0.0f);
+    float s = u - floorf(u);
+    float r = v - floorf(v);
+    if (!(s >= 0.0f && s <= 1.0f)) s = 0.0f;
+    if (!(r >= 0.0f && r <= 1.0f)) r = 0.0f;
+    const float fx = s * (float)w - 0.5f;
+    const float fy = r * (float)h - 0.5f;
+    const float flx = floorf(fx), fly = floorf(fy);
+    const float ax = fx - flx, ay = fy - fly;
+    int i0 = (int)flx, j0 = (int)fly;
+    int i1 = i0 + 1, j1 = j0 + 1;
+    i0 = ((i0 % w) + w) % w;
+    i1 = ((i1 % w) + w) % w;
+    j0 = ((j0 % h) + h) % h;
+    j1 = ((j1 % h) + h) % h;
+    const uint8_t* px = sc.tex_px[t];
+    const float w00 = (1.0f - ax) * (1.0f - ay), w10 = ax * (1.0f - ay), w01 = (1.0f - ax) * ay, w11 = ax * ay;
+    return ((texel(px, w, ch, i0, j0) * w00 + texel(px, w, ch, i1, j0) * w10) + texel(px, w, ch, i0, j1) * w01) +
+           texel(px, w, ch, i1, j1) * w11;
+}
+// S:342-368
+__device__ __forceinline__ V3 triangle_texture_color(const SceneView& sc, int numTextures, int textureIndex,
+                                                     float bw, float bu, float bv, int32_t slot) {
+    const float4 s0 = __ldg(&sc.tri_shade[2 * slot + 0]);
+    const float4 s1 = __ldg(&sc.tri_shade[2 * slot + 1]);
+    const float uvx = (s0.x * bu + s0.z * bv) + s1.x * bw;
+    const float uvy = (s0.y * bu + s0.w * bv) + s1.y * bw;
+    if (textureIndex < 0 || textureIndex >= numTextures) return v3(0.0f, 0.0f, 0.0f);
+    if (textureIndex >= RT_MAX_TEXTURES) return v3(1.0f, 0.0f, 1.0f);
+    return sample_texture(sc, textureIndex, uvx, uvy);
+}
+
+// S:216-273
+__device__ __noinline__ V3 env_light(V3 dir) {
+    const V3 sunDir = normalize(v3(0.6f, 0.3f, -0.2f));
+    const float sunDot = dot(dir, sunDir);
+    const float horizonDot = dir.y;
+    const V3 zenithColor = v3(0.15f, 0.25f, 0.65f), deepOrange = v3(1.2f, 0.4f, 0.1f),
+             yellow = v3(1.0f, 0.8f, 0.3f), coolBlue = v3(0.3f, 0.4f, 0.7f), groundColor = v3(0.2f, 0.15f, 0.1f);
+    const float sunToOpposite = (dot(dir, -sunDir) + 1.0f) * 0.5f;
+    V3 horizonColor;
+    if (sunToOpposite < 0.5f)
+        horizonColor = mix(deepOrange, yellow, sunToOpposite * 2.0f);
+    else
+        horizonColor = mix(yellow, coolBlue, (sunToOpposite - 0.5f) * 2.0f);
+    const float skyGradient = smoothstep(-0.2f, 0.8f, horizonDot);
+    const V3 baseColor = mix(horizonColor, zenithColor, skyGradient);
+    const V3 sunCenter = v3(15.0f, 15.0f, 10.0f);
+    const float sunAngle = acos_(gclamp(sunDot, -1.0f, 1.0f));
+    const float glow1 = exp_(-sunAngle * 600.0f);
+    const float glow2 = exp_(-sunAngle * 150.0f) * 0.3f;
+    const float glow3 = exp_(-sunAngle * 60.0f) * 0.1f;
+    const float glow4 = exp_(-sunAngle * 15.0f) * 0.03f;
+    const float totalGlow = ((glow1 + glow2) + glow3) + glow4;
+    V3 finalColor = baseColor + sunCenter * totalGlow;
+    if (horizonDot < 0.0f) {
+        const float groundBlend = smoothstep(-0.1f, 0.0f, horizonDot);
+        finalColor = mix(groundColor, finalColor, groundBlend);
+        const float groundSunGlow = exp_(-sunAngle * 15.0f) * 0.2f;
+        finalColor = finalColor + (sunCenter * groundSunGlow) * 0.05f;
+    }
+    return finalColor;
+}
+
+// S:201-214
+__device__ __forceinline__ V3 refract_(V3 I, V3 N, float eta, bool& isRefracted) {
+    const float k = 1.0f - eta * eta * (1.0f - dot(N, I) * dot(N, I));
+    if (k < 0.0f) {
+        isRefracted = false;
+        return reflect(I, N);
+    }
+    isRefracted = true;
+    return I * eta - N * (eta * dot(N, I) + sqrtf(k));
+}
+__device__ __forceinline__ bool black_checker(V3 p, float scale) {  // S:524-527
+    if (!(scale > 0.0f)) return false;
+    const float sum = (floorf(p.x * scale) + floorf(p.y * scale)) + floorf(p.z * scale);
+    const float m = sum - 2.0f * floorf(sum / 2.0f);
+    return m == 0.0f;
+}
+__device__ __forceinline__ V3 tri_normal(const SceneView& sc, int32_t slot) {  // S:331
+    const float4 g2 = __ldg(&sc.tri_geom[3 * slot + 2]);
+    return normalize(v3(g2.y, g2.z, g2.w));
+}
+
+// pixel geometry shared by raygen / first-hit / preview (S:663-676)
+struct PixelSetup {
+    V3 endPoint, centreDir;
+    uint32_t seed, pixelId;
+};
+__device__ __forceinline__ PixelSetup pixel_setup(const rt_uniforms& u, int tx, int ty) {
+    const int W = (int)u.width, H = (int)u.height;
+    const float x = (float)(tx * 2 - W) / (float)W;
+    const float y = (float)(ty * 2 - H) / (float)H;
+    PixelSetup ps;
+    ps.pixelId = (uint32_t)tx + (uint32_t)ty * (uint32_t)W;
+    ps.seed = ps.pixelId + u.frameIndex * 968824447u;
+    const V3 cam = v3(u.cameraPos), vf = v3(u.viewportFront), vr = v3(u.viewportRight), vu = v3(u.viewportUp);
+    ps.endPoint = ((cam + vf) + vr * x) + vu * y;
+    ps.centreDir = normalize((vf + vr * x) + vu * y);
+    return ps;
+}
+template <class R>
+__device__ __forceinline__ void sample_ray(const rt_uniforms& u, const PixelSetup& ps, R& rng, V3& o, V3& d) {
+    const float angle = rng.next();  // S:163
+    const float cx = cos01(angle), sy = sin01(angle);
+    o = (v3(u.cameraPos) + v3(u.defocusDiskRight) * cx) + v3(u.defocusDiskUp) * sy;
+    const float jr = -0.5f + (0.5f - -0.5f) * rng.next();  // random(-0.5, 0.5, seed), S:156-159
+    const float ju = -0.5f + (0.5f - -0.5f) * rng.next();
+    const V3 endJ = (ps.endPoint + v3(u.pixelRight) * jr) + v3(u.pixelUp) * ju;
+    d = normalize(endJ - o);
+}
+__device__ __forceinline__ void local_pixel_xy(const FrameParams& fp, int p, int& tx, int& ty) {
+    const int r = p / fp.width;
+    tx = p - r * fp.width;
+    ty = fp.rows ? fp.rows[r] : r;
+}
+
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kBlock) k_seed_pixels(const __grid_constant__ FrameParams fp,
+                                                        uint32_t* __restrict__ pix_rng) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= fp.local_pixels) return;
+    int tx, ty;
+    local_pixel_xy(fp, p, tx, ty);
+    pix_rng[p] = (uint32_t)tx + (uint32_t)ty * fp.u.width + fp.u.frameIndex * 968824447u;
+}
+
+__global__ void __launch_bounds__(kBlock) k_clear_accum(float4* __restrict__ accum, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) accum[i] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(kBlock) k_raygen(const __grid_constant__ FrameParams fp, PathArrays cur,
+                                                   float4* __restrict__ contrib, uint32_t* __restrict__ pix_rng,
+                                                   uint32_t* __restrict__ counts, int ncounts,
+                                                   unsigned long long* __restrict__ stats) {
+    const int n = fp.local_pixels * fp.lanes_active;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0) {
+        counts[0] = (uint32_t)n;
+        for (int k = 1; k < ncounts; k++) counts[k] = 0u;
+        atomicAdd(&stats[1], (unsigned long long)n);
+    }
+    if (i >= n) return;
+    const int lane = i / fp.local_pixels;
+    const int p = i - lane * fp.local_pixels;
+    int tx, ty;
+    local_pixel_xy(fp, p, tx, ty);
+    const PixelSetup ps = pixel_setup(fp.u, tx, ty);
+    Rng<MODE> rng;
+    rng.init(MODE == 0 ? pix_rng[p] : (uint32_t)(fp.sample_base + lane), ps.pixelId, fp.u.frameIndex, 0u);
+    rng.stream(0u);
+    V3 o, d;
+    sample_ray(fp.u, ps, rng, o, d);
+    cur.od0[i] = make_float4(o.x, o.y, o.z, d.x);
+    cur.od1[i] = make_float4(d.y, d.z, 1.0f, 1.0f);
+    cur.misc[i] = make_float4(1.0f, __int_as_float(i), __uint_as_float(rng.carry()), __int_as_float(0));
+    contrib[i] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+}
+
+template <bool COUNT>
+__global__ void __launch_bounds__(kBlock) k_extend(const __grid_constant__ SceneView sc, PathArrays cur,
+                                                   float4* __restrict__ hit, const uint32_t* __restrict__ count,
+                                                   unsigned long long* __restrict__ stats) {
+    const uint32_t n = *count;
+    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&stats[0], (unsigned long long)n);
+    uint32_t visits = 0, tests = 0;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const float4 a = cur.od0[i];
+        const float4 b = cur.od1[i];
+        const HitRec h = closest_hit<COUNT>(sc, v3(a.x, a.y, a.z), v3(a.w, b.x, b.y), visits, tests);
+        hit[i] = make_float4(h.t, h.u, h.v, __int_as_float(h.slot));
+    }
+    if (COUNT) {
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            visits += __shfl_xor_sync(0xffffffffu, visits, off);
+            tests += __shfl_xor_sync(0xffffffffu, tests, off);
+        }
+        if ((threadIdx.x & 31) == 0) {
+            atomicAdd(&stats[2], (unsigned long long)visits);
+            atomicAdd(&stats[3], (unsigned long long)tests);
+        }
+    }
+}
+
+// One bounce of S:481-560 for every live path.  `bounce` is the 0-based index of this segment.
+template <int MODE>
+__global__ void __launch_bounds__(kBlock) k_shade(const __grid_constant__ SceneView sc,
+                                                  const __grid_constant__ FrameParams fp, PathArrays cur,
+                                                  PathArrays next, const float4* __restrict__ hit,
+                                                  float4* __restrict__ contrib, uint32_t* __restrict__ pix_rng,
+                                                  const uint32_t* __restrict__ countIn,
+                                                  uint32_t* __restrict__ countOut, int bounce) {
+    const uint32_t n = *countIn;
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t stride = gridDim.x * blockDim.x;
+    for (uint32_t base = blockIdx.x * blockDim.x + (threadIdx.x & ~31u); base < n; base += stride) {
+        const uint32_t i = base + lane;
+        const bool valid = i < n;
+        bool alive = false;
+        V3 o = v3(0, 0, 0), d = v3(0, 0, 1), rayColor = v3(0, 0, 0);
+        int32_t slotId = 0;
+        uint32_t carry = 0, flags = 0;
+        if (valid) {
+            const float4 a = cur.od0[i], b = cur.od1[i], c = cur.misc[i], h = hit[i];
+            o = v3(a.x, a.y, a.z);
+            d = v3(a.w, b.x, b.y);
+            rayColor = v3(b.z, b.w, c.x);
+            slotId = __float_as_int(c.y);
+            carry = __float_as_uint(c.z);
+            flags = __float_as_uint(c.w);
+            bool insideGlass = (flags >> 16) & 1u;
+            const int bounceCount = bounce + 1;  // S:483
+            const int pixLocal = slotId % fp.local_pixels;
+            int tx, ty;
+            local_pixel_xy(fp, pixLocal, tx, ty);
+            Rng<MODE> rng;
+            rng.init(carry, (uint32_t)tx + (uint32_t)ty * fp.u.width, fp.u.frameIndex, 0u);
+            rng.stream((uint32_t)bounceCount);
+
+            const int32_t hslot = __float_as_int(h.w);
+            bool terminated = false;
+            V3 radiance = v3(0.0f, 0.0f, 0.0f);
+            if (hslot >= 0) {
+                const float dst = h.x, bu = h.y, bv = h.z;
+                const float4 s1 = __ldg(&sc.tri_shade[2 * hslot + 1]);
+                const Material m = load_material(sc, __float_as_int(s1.z));
+                const V3 hitPoint = o + d * dst;        // S:330
+                const V3 normal = tri_normal(sc, hslot);
+                if (m.type != RT_MAT_GLASS)
+                    o = hitPoint - (d * dst) * -1e-3f;  // S:490
+                else
+                    o = hitPoint + (d * dst) * -1e-3f;  // S:492
+                V3 attenuation = v3(0.0f, 0.0f, 0.0f);
+                const V3 prevDirection = d;
+                switch (m.type) {
+                    case RT_MAT_DIFFUSE:
+                    case RT_MAT_TEXTURE: {
+                        d = normalize(normal + random_direction(rng));
+                        if (m.type == RT_MAT_DIFFUSE)
+                            attenuation = m.color;
+                        else
+                            attenuation = triangle_texture_color(sc, fp.u.numTextures, m.textureIndex,
+                                                                 (1.0f - bu) - bv, bu, bv, hslot);
+                        break;
+                    }
+                    case RT_MAT_SPECULAR: {
+                        const V3 diffuseDirection = normalize(normal + random_direction(rng));
+                        const V3 specularDirection = reflect(d, normal);
+                        const bool isSpecularBounce = m.specularProbability > rng.next();
+                        d = mix(diffuseDirection, specularDirection, isSpecularBounce ? m.smoothness : 0.0f);
+                        attenuation = isSpecularBounce ? v3(1.0f, 1.0f, 1.0f) : m.color;
+                        break;
+                    }
+                    case RT_MAT_LIGHT: {
+                        const V3 emitted = m.emission * m.emissionStrength;
+                        radiance = v3(0.0f, 0.0f, 0.0f) + emitted * rayColor;  // S:516-517
+                        terminated = true;
+                        break;
+                    }
+                    case RT_MAT_CHECKER: {
+                        d = normalize(normal + random_direction(rng));
+                        attenuation = black_checker(o, m.checkerScale) ? v3(0.0f, 0.0f, 0.0f) : v3(1.0f, 1.0f, 1.0f);
+                        break;
+                    }
+                    case RT_MAT_GLASS: {
+                        const float ri = insideGlass ? m.refractiveIndex : 1.0f / m.refractiveIndex;
+                        bool isRefracted;
+                        d = refract_(d, normal, ri, isRefracted);
+                        insideGlass = isRefracted != insideGlass;
+                        attenuation = m.color;
+                        break;
+                    }
+                    default:
+                        radiance = v3(1.0f, 0.0f, 1.0f);  // S:540
+                        terminated = true;
+                        break;
+                }
+                if (!terminated) {
+                    if (m.isEdgeHighlight != 0 && bounceCount > 1)
+                        d = prevDirection;
+                    else
+                        rayColor = rayColor * attenuation;
+                    const float p = gmax(rayColor.x, gmax(rayColor.y, rayColor.z));  // S:549-552
+                    if (rng.next() > p) {
+                        terminated = true;
+                    } else {
+                        rayColor = rayColor * (1.0f / p);
+                        if (bounceCount >= fp.u.maxBounceCount) terminated = true;  // loop condition S:481
+                    }
+                }
+            } else {
+                if (fp.u.environmentalLight != 0) radiance = v3(0.0f, 0.0f, 0.0f) + env_light(d) * rayColor;
+                terminated = true;
+            }
+            carry = rng.carry();
+            if (terminated) {
+                contrib[slotId] = make_float4(radiance.x, radiance.y, radiance.z, 0.0f);
+                if (MODE == 0) pix_rng[pixLocal] = carry;  // the pixel's stream continues with the next sample
+            } else {
+                alive = true;
+                flags = (uint32_t)bounceCount | ((insideGlass ? 1u : 0u) << 16);
+            }
+        }
+        // compaction: survivors of this warp take consecutive places in the next queue
+        const uint32_t mask = __ballot_sync(0xffffffffu, alive);
+        if (mask) {
+            uint32_t basePos = 0;
+            const int leader = __ffs(mask) - 1;
+            if ((int)lane == leader) basePos = atomicAdd(countOut, (uint32_t)__popc(mask));
+            basePos = __shfl_sync(0xffffffffu, basePos, leader);
+            if (alive) {
+                const uint32_t pos = basePos + __popc(mask & ((1u << lane) - 1u));
+                next.od0[pos] = make_float4(o.x, o.y, o.z, d.x);
+                next.od1[pos] = make_float4(d.y, d.z, rayColor.x, rayColor.y);
+                next.misc[pos] = make_float4(rayColor.z, __int_as_float(slotId), __uint_as_float(carry),
+                                             __uint_as_float(flags));
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kBlock) k_accumulate(const __grid_constant__ FrameParams fp,
+                                                       const float4* __restrict__ contrib,
+                                                       float4* __restrict__ accum) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= fp.local_pixels) return;
+    float4 acc = accum[p];
+    for (int lane = 0; lane < fp.lanes_active; lane++) {  // sample order (S:683-694)
+        const float4 c = contrib[(size_t)lane * fp.local_pixels + p];
+        acc.x = acc.x + c.x;
+        acc.y = acc.y + c.y;
+        acc.z = acc.z + c.z;
+    }
+    accum[p] = acc;
+}
+
+__global__ void __launch_bounds__(kBlock) k_resolve(const __grid_constant__ FrameParams fp,
+                                                    const float4* __restrict__ accum, float4* __restrict__ image,
+                                                    uint32_t* __restrict__ frame_sum, int add_to_sum) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= fp.local_pixels) return;
+    int tx, ty;
+    local_pixel_xy(fp, p, tx, ty);
+    const float4 a = accum[p];
+    const float nr = (float)fp.u.numRaysPerPixel;
+    V3 color = v3(a.x / nr, a.y / nr, a.z / nr);  // S:696
+    color = tonemap_srgb(color);                  // S:697
+    const size_t pix = (size_t)ty * fp.width + tx;
+    image[pix] = make_float4(color.x, color.y, color.z, 1.0f);  // S:700
+    if (add_to_sum) {
+        frame_sum[pix * 3 + 0] += quantize8(color.x);
+        frame_sum[pix * 3 + 1] += quantize8(color.y);
+        frame_sum[pix * 3 + 2] += quantize8(color.z);
+    }
+}
+
+// R:248-259
+__global__ void __launch_bounds__(kBlock) k_finalize(const uint32_t* __restrict__ frame_sum, uint8_t* __restrict__ out,
+                                                     int w, int h, int frames) {
+    const size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t rowLen = (size_t)w * 3;
+    if (j >= rowLen * h) return;
+    const size_t y = j / rowLen, x = j - y * rowLen;
+    const float avg = (float)frame_sum[j] / (float)frames;
+    const float c = avg < 255.0f ? avg : 255.0f;
+    out[(size_t)(h - 1 - y) * rowLen + x] = (uint8_t)c;
+}
+
+__device__ __forceinline__ V3 normalize_color(V3 c) {  // S:462-470
+    const float m = gmax(gmax(c.x, c.y), c.z);
+    if (m > 1.0f) return c / m;
+    return c;
+}
+
+// S:565-645: preview shading, deterministic centre ray, one thread per pixel
+__global__ void __launch_bounds__(kBlock) k_preview(const __grid_constant__ SceneView sc,
+                                                    const __grid_constant__ FrameParams fp,
+                                                    float4* __restrict__ image,
+                                                    unsigned long long* __restrict__ stats) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= fp.local_pixels) return;
+    int tx, ty;
+    local_pixel_xy(fp, p, tx, ty);
+    const PixelSetup ps = pixel_setup(fp.u, tx, ty);
+    V3 o = v3(fp.u.cameraPos), d = ps.centreDir;
+    bool insideGlass = false;
+    V3 cum = v3(0.0f, 0.0f, 0.0f);
+    int bounceCount = 0;
+    uint32_t nv = 0, nt = 0, segs = 0;
+    V3 result = v3(0.0f, 0.0f, 0.0f);
+    bool done = false;
+    while (bounceCount < fp.u.maxBounceCount && !done) {
+        bounceCount++;
+        const HitRec h = closest_hit<false>(sc, o, d, nv, nt);
+        segs++;
+        if (h.slot >= 0) {
+            const V3 hitPoint = o + d * h.t;
+            const V3 normal = tri_normal(sc, h.slot);
+            o = hitPoint - normal * 1e-4f;
+            const float4 s1 = __ldg(&sc.tri_shade[2 * h.slot + 1]);
+            const Material m = load_material(sc, __float_as_int(s1.z));
+            switch (m.type) {
+                case RT_MAT_SPECULAR:
+                    cum = cum + m.color;
+                    d = reflect(d, normal);
+                    break;
+                case RT_MAT_DIFFUSE:
+                case RT_MAT_TEXTURE:
+                case RT_MAT_CHECKER: {
+                    V3 color;
+                    if (m.type == RT_MAT_TEXTURE)
+                        color = triangle_texture_color(sc, fp.u.numTextures, m.textureIndex, (1.0f - h.u) - h.v,
+                                                       h.u, h.v, h.slot);
+                    else if (m.type == RT_MAT_DIFFUSE)
+                        color = m.color;
+                    else
+                        color = black_checker(o, m.checkerScale) ? v3(0.0f, 0.0f, 0.0f) : v3(1.0f, 1.0f, 1.0f);
+                    cum = cum + color;
+                    if (fp.u.basicShadingShadow != 0) {
+                        const V3 toLight = normalize(v3(fp.u.basicShadingLightPosition) - hitPoint);
+                        const HitRec sh = closest_hit<false>(sc, o, toLight, nv, nt);
+                        segs++;
+                        const V3 c = sh.slot >= 0 ? cum / 5.0f : cum;
+                        result = c / (float)bounceCount;
+                    } else {
+                        result = cum / (float)bounceCount;
+                    }
+                    done = true;
+                    break;
+                }
+                case RT_MAT_LIGHT:
+                    result = normalize_color(m.emission);
+                    done = true;
+                    break;
+                case RT_MAT_GLASS: {
+                    const float ri = insideGlass ? m.refractiveIndex : 1.0f / m.refractiveIndex;
+                    bool isRefracted;
+                    d = refract_(d, normal, ri, isRefracted);
+                    insideGlass = isRefracted != insideGlass;
+                    cum = m.color;
+                    break;
+                }
+                case RT_MAT_GLASS_HIGHLIGHT:
+                    break;
+                default:
+                    result = v3(1.0f, 0.0f, 1.0f);
+                    done = true;
+                    break;
+            }
+        } else {
+            cum = cum + env_light(d);
+            break;
+        }
+    }
+    if (!done) result = cum / (float)bounceCount;
+    image[(size_t)ty * fp.width + tx] = make_float4(result.x, result.y, result.z, 1.0f);
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) segs += __shfl_xor_sync(0xffffffffu, segs, off);
+    if ((threadIdx.x & 31) == 0) atomicAdd(&stats[0], (unsigned long long)segs);
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(kBlock) k_first_hit(const __grid_constant__ SceneView sc,
+                                                      const __grid_constant__ FrameParams fp, int mode,
+                                                      int32_t* __restrict__ tri_id, float* __restrict__ dst) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= fp.width * fp.height) return;
+    const int ty = p / fp.width, tx = p - ty * fp.width;
+    const PixelSetup ps = pixel_setup(fp.u, tx, ty);
+    V3 o, d;
+    if (mode == RT_FIRST_HIT_CENTRE) {
+        o = v3(fp.u.cameraPos);
+        d = ps.centreDir;
+    } else {
+        Rng<MODE> rng;
+        rng.init(MODE == 0 ? ps.seed : 0u, ps.pixelId, fp.u.frameIndex, 0u);
+        rng.stream(0u);
+        sample_ray(fp.u, ps, rng, o, d);
+    }
+    uint32_t nv = 0, nt = 0;
+    const HitRec h = closest_hit<false>(sc, o, d, nv, nt);
+    tri_id[p] = h.slot >= 0 ? __ldg(&sc.tri_orig[h.slot]) : -1;
+    dst[p] = h.t;
+}
+
+template <bool COUNT>
+__global__ void __launch_bounds__(kBlock) k_trace_rays(const __grid_constant__ SceneView sc,
+                                                       const float* __restrict__ o3, const float* __restrict__ d3,
+                                                       long long n, int32_t* __restrict__ tri, float* __restrict__ dst,
+                                                       float* __restrict__ bu, float* __restrict__ bv,
+                                                       unsigned long long* __restrict__ stats) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t nv = 0, nt = 0;
+    if (i < n) {
+        const HitRec h = closest_hit<COUNT>(sc, v3(o3 + 3 * i), v3(d3 + 3 * i), nv, nt);
+        if (tri) tri[i] = h.slot >= 0 ? __ldg(&sc.tri_orig[h.slot]) : -1;
+        if (dst) dst[i] = h.t;
+        if (bu) bu[i] = h.slot >= 0 ? h.u : 0.0f;
+        if (bv) bv[i] = h.slot >= 0 ? h.v : 0.0f;
+    }
+    if (COUNT) {
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            nv += __shfl_xor_sync(0xffffffffu, nv, off);
+            nt += __shfl_xor_sync(0xffffffffu, nt, off);
+        }
+        if ((threadIdx.x & 31) == 0) {
+            atomicAdd(&stats[2], (unsigned long long)nv);
+            atomicAdd(&stats[3], (unsigned long long)nt);
+        }
+    }
+}
+
+// tile-split plumbing: compact (own rows only) <-> full-frame layouts of the 8-bit frame sums
+__global__ void __launch_bounds__(kBlock) k_rows_copy(const uint32_t* __restrict__ src, uint32_t* __restrict__ dst,
+                                                      const int32_t* __restrict__ rows, int nrows, int rowLen,
+                                                      int scatter) {
+    const size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= (size_t)nrows * rowLen) return;
+    const size_t r = j / rowLen, x = j - r * rowLen;
+    const size_t full = (size_t)rows[r] * rowLen + x;
+    if (scatter) dst[full] = src[j]; else dst[j] = src[full];
+}
+
+// ------------------------------------------------------------------------------------------------ launchers
+static inline int nblocks(long long n, int per = kBlock) { return (int)((n + per - 1) / per); }
+
+struct Timed {
+    const Launcher& L;
+    int tag;
+    int slot;
+    Timed(const Launcher& l, int t) : L(l), tag(t), slot(-1) {
+        if (L.timing && *L.ev_used + 2 <= L.ev_cap) {
+            slot = *L.ev_used;
+            *L.ev_used += 2;
+            L.ev_tag[slot] = tag;
+            cudaEventRecord(L.ev_pool[slot], L.st);
+        }
+    }
+    ~Timed() {
+        if (slot >= 0) cudaEventRecord(L.ev_pool[slot + 1], L.st);
+    }
+};
+
+cudaError_t wf_clear_accum(const Launcher& L, const WaveBuffers& wb, int local_pixels) {
+    k_clear_accum<<<nblocks(local_pixels), kBlock, 0, L.st>>>(wb.accum, local_pixels);
+    (*L.kernel_launches)++;
+    return cudaGetLastError();
+}
+
+cudaError_t wf_seed_pixels(const Launcher& L, const SceneView&, const WaveBuffers& wb, const FrameParams& fp) {
+    k_seed_pixels<<<nblocks(fp.local_pixels), kBlock, 0, L.st>>>(fp, wb.pix_rng);
+    (*L.kernel_launches)++;
+    return cudaGetLastError();
+}
+
+cudaError_t wf_render_batch(const Launcher& L, const SceneView& sc, const WaveBuffers& wb, const FrameParams& fp) {
+    const long long n = (long long)fp.local_pixels * fp.lanes_active;
+    const int maxB = fp.u.maxBounceCount;
+    const int ncounts = maxB + 2;
+    {
+        Timed t(L, 1);
+        if (L.rng_mode == RT_RNG_REF_PCG)
+            k_raygen<0><<<nblocks(n), kBlock, 0, L.st>>>(fp, wb.cur, wb.contrib, wb.pix_rng, wb.counts, ncounts, wb.stats);
+        else
+            k_raygen<1><<<nblocks(n), kBlock, 0, L.st>>>(fp, wb.cur, wb.contrib, wb.pix_rng, wb.counts, ncounts, wb.stats);
+        (*L.kernel_launches)++;
+    }
+    // fixed-size grids that stride over the live count read on the device: no host round trip per bounce
+    const int grid = (int)((n + kBlock - 1) / kBlock < (long long)L.sm_count * 8 ? (n + kBlock - 1) / kBlock
+                                                                                : (long long)L.sm_count * 8);
+    PathArrays a = wb.cur, b = wb.next;
+    for (int bounce = 0; bounce < maxB; bounce++) {
+        {
+            Timed t(L, 0);
+            if (L.instrument)
+                k_extend<true><<<grid, kBlock, 0, L.st>>>(sc, a, wb.hit, wb.counts + bounce, wb.stats);
+            else
+                k_extend<false><<<grid, kBlock, 0, L.st>>>(sc, a, wb.hit, wb.counts + bounce, wb.stats);
+            (*L.kernel_launches)++;
+            (*L.extend_launches)++;
+        }
+        {
+            Timed t(L, 1);
+            if (L.rng_mode == RT_RNG_REF_PCG)
+                k_shade<0><<<grid, kBlock, 0, L.st>>>(sc, fp, a, b, wb.hit, wb.contrib, wb.pix_rng, wb.counts + bounce,
+                                                      wb.counts + bounce + 1, bounce);
+            else
+                k_shade<1><<<grid, kBlock, 0, L.st>>>(sc, fp, a, b, wb.hit, wb.contrib, wb.pix_rng, wb.counts + bounce,
+                                                      wb.counts + bounce + 1, bounce);
+            (*L.kernel_launches)++;
+        }
+        PathArrays tmp = a;
+        a = b;
+        b = tmp;
+    }
+    {
+        Timed t(L, 1);
+        k_accumulate<<<nblocks(fp.local_pixels), kBlock, 0, L.st>>>(fp, wb.contrib, wb.accum);
+        (*L.kernel_launches)++;
+    }
+    return cudaGetLastError();
+}
+
+cudaError_t wf_resolve_frame(const Launcher& L, const WaveBuffers& wb, const FrameParams& fp, bool add_to_sum) {
+    Timed t(L, 1);
+    k_resolve<<<nblocks(fp.local_pixels), kBlock, 0, L.st>>>(fp, wb.accum, wb.image, wb.frame_sum, add_to_sum ? 1 : 0);
+    (*L.kernel_launches)++;
+    return cudaGetLastError();
+}
+
+cudaError_t wf_preview(const Launcher& L, const SceneView& sc, const WaveBuffers& wb, const FrameParams& fp) {
+    Timed t(L, 0);
+    k_preview<<<nblocks(fp.local_pixels), kBlock, 0, L.st>>>(sc, fp, wb.image, wb.stats);
+    (*L.kernel_launches)++;
+    return cudaGetLastError();
+}
+
+cudaError_t wf_finalize(const Launcher& L, const uint32_t* frame_sum, uint8_t* out, int w, int h, int frames) {
+    Timed t(L, 1);
+    k_finalize<<<nblocks((long long)w * h * 3), kBlock, 0, L.st>>>(frame_sum, out, w, h, frames);
+    (*L.kernel_launches)++;
+    return cudaGetLastError();
+}
+
+cudaError_t wf_first_hit(const Launcher& L, const SceneView& sc, const FrameParams& fp, int mode, int32_t* tri_id,
+                         float* dst) {
+    const long long n = (long long)fp.width * fp.height;
+    if (L.rng_mode == RT_RNG_REF_PCG)
+        k_first_hit<0><<<nblocks(n), kBlock, 0, L.st>>>(sc, fp, mode, tri_id, dst);
+    else
+        k_first_hit<1><<<nblocks(n), kBlock, 0, L.st>>>(sc, fp, mode, tri_id, dst);
+    (*L.kernel_launches)++;
+    return cudaGetLastError();
+}
+
+cudaError_t wf_trace_rays(const Launcher& L, const SceneView& sc, const float* o, const float* d, int64_t n,
+                          int32_t* tri, float* dst, float* bu, float* bv, unsigned long long* stats) {
+    if (n <= 0) return cudaSuccess;
+    if (L.instrument)
+        k_trace_rays<true><<<nblocks(n), kBlock, 0, L.st>>>(sc, o, d, n, tri, dst, bu, bv, stats);
+    else
+        k_trace_rays<false><<<nblocks(n), kBlock, 0, L.st>>>(sc, o, d, n, tri, dst, bu, bv, stats);
+    (*L.kernel_launches)++;
+    return cudaGetLastError();
+}
+
+cudaError_t wf_scatter_rows(const Launcher& L, const uint32_t* compact, uint32_t* full, const int32_t* rows, int nrows,
+                            int width) {
+    if (nrows <= 0) return cudaSuccess;
+    k_rows_copy<<<nblocks((long long)nrows * width * 3), kBlock, 0, L.st>>>(compact, full, rows, nrows, width * 3, 1);
+    (*L.kernel_launches)++;
+    return cudaGetLastError();
+}
+cudaError_t wf_gather_rows(const Launcher& L, const uint32_t* full, uint32_t* compact, const int32_t* rows, int nrows,
+                           int width) {
+    if (nrows <= 0) return cudaSuccess;
+    k_rows_copy<<<nblocks((long long)nrows * width * 3), kBlock, 0, L.st>>>(full, compact, rows, nrows, width * 3, 0);
+    (*L.kernel_launches)++;
+    return cudaGetLastError();
+}
+
+}  // namespace rt

@@ -479,7 +479,7 @@ int rth_set_procedural_texture(rth_scene* s, int32_t slot, int32_t size) {
 static void cameraViewport(rth_camera* c, float mouseYOffset) {  // C:163-180
     c->zoom += mouseYOffset;
     const float h = std::tan(c->hfov / 2);
-    const float viewportWidth = 2 * h / (float)exp((double)(c->zoom * c->zoomSensitivity));
+    const float viewportWidth = 2 * h / std::exp(c->zoom * c->zoomSensitivity);
     const float viewportHeight = viewportWidth / c->aspectRatio;
     const V3 right = get3(c->right), up = get3(c->up), front = get3(c->front);
     const V3 vr = (right * viewportWidth) * c->focusDistance;
@@ -495,11 +495,12 @@ static void cameraViewport(rth_camera* c, float mouseYOffset) {  // C:163-180
     put3(c->defocusDiskUp, up * defocusRadius);
 }
 static void cameraBasis(rth_camera* c) {  // C:150-160
-    // the unqualified cos/sin of camera.h resolve to the double versions of <math.h>
+    // the unqualified cos/sin/exp of camera.h resolve to the float overloads (checked bit for bit
+    // against the compiled reference in tests/test_oracle_cpu.py)
     V3 front;
-    front.x = (float)(cos((double)c->yaw) * cos((double)c->pitch));
-    front.y = (float)sin((double)c->pitch);
-    front.z = (float)(sin((double)c->yaw) * cos((double)c->pitch));
+    front.x = std::cos(c->yaw) * std::cos(c->pitch);
+    front.y = std::sin(c->pitch);
+    front.z = std::sin(c->yaw) * std::cos(c->pitch);
     front = normalize(front);
     const V3 right = normalize(cross(get3(c->worldUp), front));
     const V3 up = normalize(cross(front, right));
@@ -564,7 +565,7 @@ void rth_camera_mouse(rth_camera* c, double xpos, double ypos) {  // C:194-213
     const float yoffset = (float)(ypos - c->lastY);
     c->lastX = xpos;
     c->lastY = ypos;
-    const float ez = (float)exp((double)(c->zoom * c->zoomSensitivity));
+    const float ez = std::exp(c->zoom * c->zoomSensitivity);
     c->pitch += yoffset / c->scrWidth * c->mouseSensitivity / ez;
     c->pitch = clampf(c->pitch, -kPI / 2.1f, kPI / 2.1f);
     c->yaw += xoffset / c->scrWidth * c->mouseSensitivity / ez;

@@ -1,0 +1,358 @@
+"""GPU parity tests (run with -m gpu on the B200 box): the CUDA path through the C-ABI against the CPU
+oracle on the same seeded inputs.  Integer / index results (triangle ids, 8-bit images, counters)
+must be bit-exact; binary32 results are also required to be bit-exact because oracle and kernels
+evaluate the same operation order without FMA contraction — the tolerance written in
+each test is therefore 0 ulp, with a PSNR floor reported alongside for the record."""
+import importlib
+
+import numpy as np
+import pytest
+
+import oracle
+
+rt = importlib.import_module("raytracing2-fork_b200")
+pytestmark = pytest.mark.gpu
+
+
+def psnr(a, b, peak=1.0):
+    mse = np.mean((a.astype(np.float64) - b.astype(np.float64)) ** 2)
+    return 99.0 if mse == 0 else 10 * np.log10(peak * peak / mse)
+
+
+def bits(a):
+    return np.ascontiguousarray(a, dtype=np.float32).view(np.uint32)
+
+
+def assert_image_equal(gpu, ref, what):
+    same = bits(gpu) == bits(ref)
+    nan_both = np.isnan(gpu) & np.isnan(ref)
+    ok = same | nan_both
+    if not ok.all():
+        bad = np.argwhere(~ok)
+        raise AssertionError(f"{what}: {bad.shape[0]} of {ok.size} floats differ, PSNR {psnr(gpu, ref):.1f} dB, "
+                             f"first at {bad[0]}: gpu {gpu[tuple(bad[0])]!r} oracle {ref[tuple(bad[0])]!r}")
+
+
+def random_rays(n, seed, lo, hi):
+    rng = np.random.default_rng(seed)
+    o = rng.uniform(lo, hi, size=(n, 3)).astype(np.float32)
+    d = rng.normal(size=(n, 3))
+    d = (d / np.linalg.norm(d, axis=1, keepdims=True)).astype(np.float32)
+    return o, d
+
+
+@pytest.fixture(scope="module")
+def classic():
+    scene = rt.scene_classic_cornell()
+    return scene, oracle.OracleScene.from_scene(scene)
+
+
+@pytest.fixture(scope="module")
+def sphere_box():
+    scene = rt.scene_textured_sphere(n_quads=40, container="cornell", tex_size=128)  # 3200 + 16 tris
+    return scene, oracle.OracleScene.from_scene(scene)
+
+
+def backend(scene, **kw):
+    be = rt.Backend(device=0, **kw)
+    be.upload(scene)
+    return be
+
+
+# ------------------------------------------------------------------------------------------------
+def test_trace_rays_bit_exact_vs_bruteforce(classic):
+    scene, orc = classic
+    be = backend(scene)
+    o, d = random_rays(20000, 1, -4.9, 4.9)
+    tri, dst, bu, bv = be.trace_rays(o, d)
+    otri, odst, obu, obv = orc.trace_rays(o, d, use_bvh=False)
+    assert np.array_equal(tri, otri)
+    assert np.array_equal(bits(dst), bits(odst))
+    assert np.array_equal(bits(bu), bits(obu)) and np.array_equal(bits(bv), bits(obv))
+    assert (tri >= 0).mean() > 0.99  # closed box: (almost) every ray hits
+
+
+def test_trace_rays_sphere_scene_vs_bruteforce(sphere_box):
+    scene, orc = sphere_box
+    be = backend(scene)
+    o, d = random_rays(4000, 2, -3.5, 3.5)
+    tri, dst, bu, bv = be.trace_rays(o, d)
+    otri, odst, obu, obv = orc.trace_rays(o, d, use_bvh=False)
+    assert np.array_equal(tri, otri)
+    assert np.array_equal(bits(dst), bits(odst))
+    assert np.array_equal(bits(bu), bits(obu)) and np.array_equal(bits(bv), bits(obv))
+
+
+def test_ties_resolve_to_lowest_index():
+    # duplicate geometry on purpose (addSkyLightPlane inserts its triangles twice, rayTracing.cpp:428-431)
+    s = rt.Scene()
+    red = s.add_fixed_materials()
+    s.add_cube((0, 0, 0), (2, 2, 2), (0, 0, 0), red + 2)
+    tris = s.triangles
+    s.add_triangles(tris)          # exact duplicates with higher indices
+    s.add_triangles(tris[::-1])    # and again, reversed
+    be = backend(s)
+    orc = oracle.OracleScene.from_scene(s)
+    o, d = random_rays(5000, 3, -6, 6)
+    d = (-o / np.linalg.norm(o, axis=1, keepdims=True)).astype(np.float32)  # aim at the cube
+    tri, dst, _, _ = be.trace_rays(o, d)
+    otri, odst, _, _ = orc.trace_rays(o, d, use_bvh=False)
+    assert np.array_equal(tri, otri)
+    assert tri.max() < 12  # always the first copy
+
+
+@pytest.mark.parametrize("mode", [rt.FIRST_HIT_CENTRE, rt.FIRST_HIT_SAMPLE0])
+@pytest.mark.parametrize("rng_mode", [rt.RNG_REF_PCG, rt.RNG_PHILOX])
+def test_first_hit_config1_512(classic, mode, rng_mode):
+    """BASELINE config 1 at full size: 512x512 first-hit ids, bit-exact."""
+    scene, orc = classic
+    cam = rt.make_camera(512, 512, (0.0, 0.0, 15.5))
+    u = rt.screenshot_uniforms(scene, cam, spp=64, max_bounce=8, env_light=False, frame_index=3)
+    be = backend(scene, rng_mode=rng_mode)
+    tri, dst = be.first_hit(u, mode)
+    otri, odst = orc.first_hit(u, mode, rng_mode=rng_mode)
+    assert np.array_equal(tri, otri)
+    assert np.array_equal(bits(dst), bits(odst))
+    assert (tri >= 0).mean() > 0.95
+
+
+def test_first_hit_sphere_scene(sphere_box):
+    scene, orc = sphere_box
+    cam = rt.camera_for_box(scene, 320, 180)
+    u = rt.screenshot_uniforms(scene, cam, spp=4, max_bounce=4, env_light=False)
+    be = backend(scene)
+    for mode in (rt.FIRST_HIT_CENTRE, rt.FIRST_HIT_SAMPLE0):
+        tri, dst = be.first_hit(u, mode)
+        otri, odst = orc.first_hit(u, mode, rng_mode=rt.RNG_PHILOX)
+        assert np.array_equal(tri, otri)
+        assert np.array_equal(bits(dst), bits(odst))
+    assert len(np.unique(tri)) > 300  # the sphere is actually in view
+
+
+def test_bvh_is_valid(sphere_box):
+    scene, _ = sphere_box
+    be = backend(scene)
+    nodes, ids, lo, hi = be.get_bvh()
+    t = scene.triangles
+    n = t.size
+    assert nodes.size == n - 1 and ids.size == n
+    assert sorted(ids.tolist()) == list(range(n))  # a permutation
+    pts = np.stack([t["a"][:, :3], t["b"][:, :3], t["c"][:, :3]], axis=1)
+    tlo, thi = pts.min(1), pts.max(1)
+    assert np.allclose(lo, tlo.min(0)) and np.allclose(hi, thi.max(0))
+    seen = np.zeros(n, dtype=bool)
+    # every leaf box contains its triangles; every inner child box contains the boxes below it
+    def box(node, k):
+        return (np.array([node["lo_x"][k], node["lo_y"][k], node["lo_z"][k]]),
+                np.array([node["hi_x"][k], node["hi_y"][k], node["hi_z"][k]]))
+    def visit(i):
+        lo_acc, hi_acc = np.full(3, np.inf), np.full(3, -np.inf)
+        for k in range(2):
+            blo, bhi = box(nodes[i], k)
+            c = int(nodes[i]["child"][k])
+            if c < 0:
+                first, cnt = ~c, int(nodes[i]["count"][k])
+                for s in range(first, first + cnt):
+                    tid = ids[s]
+                    assert not seen[tid]
+                    seen[tid] = True
+                    assert (tlo[tid] >= blo).all() and (thi[tid] <= bhi).all()
+            else:
+                clo, chi = visit(c)
+                assert (clo >= blo - 1e-6).all() and (chi <= bhi + 1e-6).all()
+            lo_acc, hi_acc = np.minimum(lo_acc, blo), np.maximum(hi_acc, bhi)
+        return lo_acc, hi_acc
+    import sys
+    sys.setrecursionlimit(10000)
+    rlo, rhi = visit(0)
+    assert seen.all()
+    assert (rlo <= tlo.min(0)).all() and (rhi >= thi.max(0)).all()
+    assert be.counters()["bvh_depth"] < 64
+
+
+@pytest.mark.parametrize("rng_mode", [rt.RNG_REF_PCG, rt.RNG_PHILOX])
+def test_frame_classic_cornell_bit_exact(classic, rng_mode):
+    scene, orc = classic
+    cam = rt.make_camera(96, 96, (0.0, 0.0, 15.5))
+    u = rt.screenshot_uniforms(scene, cam, spp=16, max_bounce=8, env_light=False, frame_index=1)
+    be = backend(scene, rng_mode=rng_mode)
+    be.render_frame(u)
+    img = be.read_frame()
+    cn = oracle.OrcCounters()
+    ref = orc.render_frame(u, rng_mode=rng_mode, counters=cn)
+    assert_image_equal(img, ref, "classic cornell frame")
+    c = be.counters()
+    assert c["segments"] == cn.segments and c["paths"] == cn.paths  # same number of rays traced
+    assert img[..., :3].max() > 0.2  # the light is visible
+
+
+@pytest.mark.parametrize("rng_mode", [rt.RNG_REF_PCG, rt.RNG_PHILOX])
+@pytest.mark.parametrize("container", ["cornell", "mirror"])
+def test_frame_textured_sphere_bit_exact(rng_mode, container):
+    scene = rt.scene_textured_sphere(n_quads=24, container=container, tex_size=64)
+    orc = oracle.OracleScene.from_scene(scene)
+    cam = rt.camera_for_box(scene, 96, 54)
+    u = rt.screenshot_uniforms(scene, cam, spp=8, max_bounce=12, env_light=False)
+    be = backend(scene, rng_mode=rng_mode)
+    be.render_frame(u)
+    img = be.read_frame()
+    ref = orc.render_frame(u, rng_mode=rng_mode)
+    assert_image_equal(img, ref, f"textured sphere in {container} box")
+
+
+def test_frame_with_small_path_budget_is_identical(classic):
+    """Lanes per pixel (how many samples are in flight together) must not change a single bit."""
+    scene, orc = classic
+    cam = rt.make_camera(64, 64, (0.0, 0.0, 15.5))
+    u = rt.screenshot_uniforms(scene, cam, spp=10, max_bounce=6, env_light=False)
+    ref = orc.render_frame(u, rng_mode=rt.RNG_PHILOX)
+    for budget in (64 * 64, 64 * 64 * 3, 64 * 64 * 16):
+        be = backend(scene, max_paths_in_flight=budget)
+        be.render_frame(u)
+        assert_image_equal(be.read_frame(), ref, f"budget {budget}")
+
+
+def test_all_material_types_and_env_light():
+    """CHECKER, GLASS, partial-smoothness SPECULAR, edge highlight, GLASS_HIGHLIGHT (magenta in trace),
+    and the procedural sky on a miss (compute.glsl:216-273, 521-546)."""
+    s = rt.Scene()
+    red = s.add_fixed_materials()
+    glass = s.add_glass((0.9, 0.95, 1.0), 1.5)
+    checker = s.add_checker(2.0)
+    metal = s.add_specular((0.8, 0.6, 0.2), (1, 1, 1), 0.7, 0.5)
+    m = np.zeros(1, dtype=rt.MATERIAL)
+    m["color"] = (0.2, 0.9, 0.3, 0); m["materialType"] = rt.MAT_DIFFUSE; m["isEdgeHighlight"] = 1; m["textureIndex"] = -1
+    edge = s.add_material(m)
+    m2 = np.zeros(1, dtype=rt.MATERIAL)
+    m2["color"] = (1, 1, 0, 0); m2["materialType"] = rt.MAT_GLASS_HIGHLIGHT; m2["textureIndex"] = -1
+    gh = s.add_material(m2)
+    s.add_cube((0, -1.5, 0), (12, 0.2, 12), (0, 0, 0), checker)
+    s.add_cube((-2.5, 0, 0), (1.5, 1.5, 1.5), (0.2, 0.5, 0.1), glass)
+    s.add_cube((0, 0, -1), (1.5, 1.5, 1.5), (0.0, 0.8, 0.3), metal)
+    s.add_cube((2.5, 0, 0), (1.5, 1.5, 1.5), (0.4, 0.1, 0.0), edge)
+    s.add_cube((0, 1.5, -3), (1, 1, 1), (0, 0, 0), gh)
+    s.add_cube((0, 3.5, 0), (2, 0.1, 2), (0, 0, 0), red + 3)
+    orc = oracle.OracleScene.from_scene(s)
+    cam = rt.make_camera(96, 64, (0.0, 1.0, 12.0), pitch=0.05)
+    for rng_mode in (rt.RNG_REF_PCG, rt.RNG_PHILOX):
+        u = rt.screenshot_uniforms(s, cam, spp=8, max_bounce=10, env_light=True)
+        be = backend(s, rng_mode=rng_mode)
+        be.render_frame(u)
+        assert_image_equal(be.read_frame(), orc.render_frame(u, rng_mode=rng_mode), "material zoo")
+
+
+def test_defocus_and_preview(classic):
+    scene, orc = classic
+    cam = rt.make_camera(80, 80, (0.0, 0.0, 15.5), defocus=0.05)
+    u = rt.screenshot_uniforms(scene, cam, spp=8, max_bounce=5, env_light=False)
+    be = backend(scene, rng_mode=rt.RNG_REF_PCG)
+    be.render_frame(u)
+    assert_image_equal(be.read_frame(), orc.render_frame(u, rng_mode=rt.RNG_REF_PCG), "defocus frame")
+    # interactive preview (traceBasic), with and without the shadow ray
+    for shadow in (0, 1):
+        up = rt.interactive_uniforms(scene, cam)
+        up["basicShadingShadow"] = shadow
+        be.render_frame(up)
+        assert_image_equal(be.read_frame(), orc.render_frame(up), f"preview shadow={shadow}")
+
+
+@pytest.mark.parametrize("rng_mode", [rt.RNG_REF_PCG, rt.RNG_PHILOX])
+def test_screenshot_rgb8_identical(classic, rng_mode):
+    scene, orc = classic
+    cam = rt.make_camera(64, 48, (0.0, 0.0, 15.5))
+    u = rt.screenshot_uniforms(scene, cam, spp=8, max_bounce=8, env_light=False)
+    be = backend(scene, rng_mode=rng_mode)
+    shot = be.screenshot(u, 3)
+    ref, sums = orc.screenshot(u, 3, rng_mode=rng_mode)
+    assert np.array_equal(shot, ref)
+    assert shot.max() > 100 and shot.shape == (48, 64, 3)
+    # device-resident variant gives the same bytes
+    be.screenshot_device(u, 3)
+    assert np.array_equal(be.screenshot_fetch(), ref)
+
+
+@pytest.mark.parametrize("split", [rt.SPLIT_TILES, rt.SPLIT_FRAMES])
+def test_rank_partials_sum_to_single_gpu_result(classic, split):
+    """Multi-GPU sharding emulated rank by rank on one GPU: the partial 8-bit sums of 3 ranks add up
+    to exactly the single-rank sums (tile split: disjoint rows; frame split: exact integer sums)."""
+    scene, orc = classic
+    cam = rt.make_camera(64, 40, (0.0, 0.0, 15.5))
+    u = rt.screenshot_uniforms(scene, cam, spp=4, max_bounce=6, env_light=False)
+    frames = 5
+    single = backend(scene)
+    total = single.screenshot_partial(u, frames)
+    acc = np.zeros_like(total)
+    for rank in range(3):
+        be = backend(scene, split_mode=split, rank=rank, world_size=3, band_rows=4)
+        part = be.screenshot_partial(u, frames)
+        if split == rt.SPLIT_TILES:
+            rows = rt.split_rows(40, 4, rank, 3)
+            mask = np.zeros(40, dtype=bool); mask[rows] = True
+            assert part[~mask].sum() == 0
+        acc += part
+    assert np.array_equal(acc, total)
+    final = single.finalize_sums(acc, frames)
+    ref, osums = orc.screenshot(u, frames, rng_mode=rt.RNG_PHILOX)
+    assert np.array_equal(total, osums)
+    assert np.array_equal(final, ref)
+
+
+def test_edge_cases_and_errors():
+    L = rt.backend_lib()
+    # empty scene: everything misses, env light fills the frame
+    s = rt.Scene()
+    s.add_fixed_materials()
+    be = backend(s)
+    cam = rt.make_camera(32, 32, (0.0, 0.0, 5.0))
+    u = rt.screenshot_uniforms(s, cam, spp=2, max_bounce=3, env_light=True)
+    tri, dst = be.first_hit(u)
+    assert (tri == -1).all() and (dst == np.float32(1e38)).all()
+    orc = oracle.OracleScene.from_scene(s)
+    be.render_frame(u)
+    assert_image_equal(be.read_frame(), orc.render_frame(u, rng_mode=rt.RNG_PHILOX), "empty scene")
+    # single triangle (no inner node)
+    s1 = rt.Scene()
+    red = s1.add_fixed_materials()
+    t = np.zeros(1, dtype=rt.TRIANGLE)
+    t["a"] = (-1, -1, 0, 0); t["b"] = (1, -1, 0, 0); t["c"] = (0, 1, 0, 0); t["materialIndex"] = red + 3
+    s1.add_triangles(t)
+    be1 = backend(s1)
+    tri, _ = be1.first_hit(u)
+    assert set(np.unique(tri)) == {-1, 0}
+    o1 = oracle.OracleScene.from_scene(s1)
+    otri, _ = o1.first_hit(u, use_bvh=True)
+    assert np.array_equal(tri, otri)
+    # errors: rendering before the build, bad material index, NULL arguments
+    be2 = rt.Backend(device=0)
+    with pytest.raises(rt.BackendError):
+        be2.render_frame(u)
+    bad = s1.triangles.copy(); bad["materialIndex"] = 99
+    be2.set_triangles(bad); be2.set_materials(s1.materials)
+    with pytest.raises(rt.BackendError):
+        be2.build()
+    assert L.rt_scene_set_triangles(be2.h, None, 5) == 1  # RT_ERR_INVALID
+    assert b"bad argument" in L.rt_last_error(be2.h)
+
+
+def test_large_mesh_properties():
+    """Size-independent properties at a size the oracle cannot brute-force: 2*224^2 = 100 352
+    triangles (config 2's mesh).  (i) the BVH answer equals the oracle's BVH answer on random rays,
+    (ii) tracing is deterministic, (iii) the rendered frame does not depend on the path budget."""
+    scene = rt.scene_textured_sphere(n_quads=224, container="cornell", tex_size=256)
+    be = backend(scene)
+    orc = oracle.OracleScene.from_scene(scene)
+    o, d = random_rays(20000, 7, -4, 4)
+    tri, dst, bu, bv = be.trace_rays(o, d)
+    otri, odst, obu, obv = orc.trace_rays(o, d, use_bvh=True)
+    assert np.array_equal(tri, otri) and np.array_equal(bits(dst), bits(odst))
+    tri2, dst2, _, _ = be.trace_rays(o, d)
+    assert np.array_equal(tri, tri2) and np.array_equal(bits(dst), bits(dst2))
+    cam = rt.camera_for_box(scene, 160, 90)
+    u = rt.screenshot_uniforms(scene, cam, spp=4, max_bounce=6, env_light=False)
+    be.render_frame(u)
+    a = be.read_frame()
+    be_small = backend(scene, max_paths_in_flight=160 * 90)
+    be_small.render_frame(u)
+    assert_image_equal(be_small.read_frame(), a, "path budget independence")
+    ref = orc.render_frame(u, rng_mode=rt.RNG_PHILOX)
+    assert_image_equal(a, ref, "100k-triangle frame vs oracle")
