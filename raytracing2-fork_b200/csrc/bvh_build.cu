@@ -285,7 +285,7 @@ __global__ void __launch_bounds__(256) k_refit(const rt_triangle* __restrict__ t
                                                const int32_t* __restrict__ children,
                                                const int32_t* __restrict__ parent,
                                                float4* __restrict__ boxes, uint32_t* __restrict__ flags,
-                                               uint32_t* __restrict__ maxDepth) {
+                                               uint32_t* __restrict__ nodeDepth, uint32_t* __restrict__ maxDepth) {
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= n) return;
     const rt_triangle& t = tris[sortedIdx[s]];
@@ -309,8 +309,12 @@ __global__ void __launch_bounds__(256) k_refit(const rt_triangle* __restrict__ t
     int node = parent[n - 1 + s];
     uint32_t depth = 1;
     while (node >= 0) {
+        // both arrivals deposit the height of their subtree; the second one continues with the max
+        atomicMax(&nodeDepth[node], depth);
+        __threadfence();
         if (atomicAdd(&flags[node], 1u) == 0u) return;  // first arrival: the sibling is not ready yet
         __threadfence();
+        depth = __ldcg(&nodeDepth[node]);
         const int32_t cl = children[2 * node], cr = children[2 * node + 1];
         const int el = cl >= 0 ? cl : (n - 1 + ~cl), er = cr >= 0 ? cr : (n - 1 + ~cr);
         // the sibling's box was written by another SM: read through L2, never a stale L1 line
@@ -394,11 +398,12 @@ cudaError_t build_lbvh(const BuildArgs& a, cudaStream_t st, uint64_t* launches) 
         // 8 passes: the result is back in buffer 0
         k_hierarchy<<<nb(n - 1, 256), 256, 0, st>>>(a.keys[0], n, a.children, a.parent); L++;
         cudaMemsetAsync(a.flags, 0, sizeof(uint32_t) * (size_t)(n - 1), st);
+        cudaMemsetAsync(a.nodeDepth, 0, sizeof(uint32_t) * (size_t)(n - 1), st);
     } else {
         k_iota<<<1, 32, 0, st>>>(a.vals[0], n); L++;
     }
     k_refit<<<nb(n, 256), 256, 0, st>>>(a.tris, a.vals[0], n, a.bounds, a.children, a.parent, a.boxes, a.flags,
-                                        a.maxDepth); L++;
+                                        a.nodeDepth, a.maxDepth); L++;
     if (n >= 2) { k_emit_nodes<<<nb(n - 1, 256), 256, 0, st>>>(n, a.children, a.boxes, a.nodes); L++; }
     k_emit_tris<<<nb(n, 256), 256, 0, st>>>(a.tris, a.vals[0], n, a.geom, a.shade, a.orig); L++;
     if (launches) *launches += L;

@@ -114,7 +114,7 @@ struct rt_ctx {
     DevBuf d_tris, d_mats, d_tex[RT_MAX_TEXTURES];
     int tex_w[RT_MAX_TEXTURES] = {0}, tex_h[RT_MAX_TEXTURES] = {0}, tex_ch[RT_MAX_TEXTURES] = {0};
     // build scratch + outputs
-    DevBuf d_centroid, d_bounds, d_keys[2], d_vals[2], d_hist, d_children, d_parent, d_boxes, d_flags, d_depth;
+    DevBuf d_centroid, d_bounds, d_keys[2], d_vals[2], d_hist, d_children, d_parent, d_boxes, d_flags, d_depth, d_node_depth;
     DevBuf d_nodes, d_geom, d_shade, d_orig;
     // wavefront
     DevBuf d_path[6], d_hit, d_contrib, d_accum, d_pixrng, d_counts, d_stats, d_image, d_sum, d_out, d_rows;
@@ -465,7 +465,7 @@ void rt_destroy(rt_ctx* ctx) {
     if (ctx->comm && nccl().ok) nccl().CommDestroy(ctx->comm);
     DevBuf* all[] = {&ctx->d_tris, &ctx->d_mats, &ctx->d_centroid, &ctx->d_bounds, &ctx->d_keys[0], &ctx->d_keys[1],
                      &ctx->d_vals[0], &ctx->d_vals[1], &ctx->d_hist, &ctx->d_children, &ctx->d_parent, &ctx->d_boxes,
-                     &ctx->d_flags, &ctx->d_depth, &ctx->d_nodes, &ctx->d_geom, &ctx->d_shade, &ctx->d_orig, &ctx->d_hit,
+                     &ctx->d_flags, &ctx->d_depth, &ctx->d_node_depth, &ctx->d_nodes, &ctx->d_geom, &ctx->d_shade, &ctx->d_orig, &ctx->d_hit,
                      &ctx->d_contrib, &ctx->d_accum, &ctx->d_pixrng, &ctx->d_counts, &ctx->d_stats, &ctx->d_image,
                      &ctx->d_sum, &ctx->d_out, &ctx->d_rows, &ctx->d_stage, &ctx->d_compact};
     for (DevBuf* b : all) b->release();
@@ -552,6 +552,7 @@ int rt_scene_build(rt_ctx* ctx) {
     CK(ctx->d_parent.reserve((size_t)(2 * n) * sizeof(int32_t)));
     CK(ctx->d_boxes.reserve((size_t)(2 * n) * 2 * sizeof(float4)));
     CK(ctx->d_flags.reserve(nn * sizeof(uint32_t)));
+    CK(ctx->d_node_depth.reserve(nn * sizeof(uint32_t)));
     CK(ctx->d_depth.reserve(sizeof(uint32_t)));
     CK(ctx->d_nodes.reserve(nn * 4 * sizeof(float4)));
     CK(ctx->d_geom.reserve((size_t)n * 3 * sizeof(float4)));
@@ -571,6 +572,7 @@ int rt_scene_build(rt_ctx* ctx) {
     a.parent = ctx->d_parent.as<int32_t>();
     a.boxes = ctx->d_boxes.as<float4>();
     a.flags = ctx->d_flags.as<uint32_t>();
+    a.nodeDepth = ctx->d_node_depth.as<uint32_t>();
     a.maxDepth = ctx->d_depth.as<uint32_t>();
     a.nodes = ctx->d_nodes.as<float4>();
     a.geom = ctx->d_geom.as<float4>();

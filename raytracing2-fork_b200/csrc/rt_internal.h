@@ -21,6 +21,7 @@ struct BuildArgs {
     int32_t* parent;          // 2n-1
     float4* boxes;            // 2*(2n-1)
     uint32_t* flags;          // n-1
+    uint32_t* nodeDepth;      // n-1 (height of the subtree under each inner node)
     uint32_t* maxDepth;       // 1
     float4* nodes;            // 4*(n-1)   (output)
     float4* geom;             // 3*n       (output)
