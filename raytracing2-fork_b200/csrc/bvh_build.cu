@@ -10,7 +10,7 @@
 //   k_hierarchy    Karras 2012: one thread per inner node finds its range and split
 //   k_refit        bottom-up AABB union with one atomic flag per inner node
 //   k_emit_nodes   64-byte nodes with both child boxes in the parent
-//   k_emit_tris    sorted triangle records: (a, e0, e1, N) | (uvs, material, orig)
+//   k_emit_tris    sorted triangle records: (a, e0, e1, N, orig, material) | (uvs, material, orig)
 // Everything is deterministic (stable sort, min/max are order independent), so every GPU of a
 // multi-GPU job builds the identical tree.
 #include "rt_internal.h"
@@ -343,9 +343,9 @@ __global__ void __launch_bounds__(256) k_emit_nodes(int n, const int32_t* __rest
     const int32_t pl = cl >= 0 ? cl : pack_leaf(~cl, 1);
     const int32_t pr = cr >= 0 ? cr : pack_leaf(~cr, 1);
     nodes[4 * i + 0] = make_float4(llo.x, lhi.x, llo.y, lhi.y);
-    nodes[4 * i + 1] = make_float4(rlo.x, rhi.x, rlo.y, rhi.y);
-    nodes[4 * i + 2] = make_float4(llo.z, lhi.z, rlo.z, rhi.z);
-    nodes[4 * i + 3] = make_float4(__int_as_float(pl), __int_as_float(pr), 0.0f, 0.0f);
+    nodes[4 * i + 1] = make_float4(llo.z, lhi.z, __int_as_float(pl), __int_as_float(pr));
+    nodes[4 * i + 2] = make_float4(rlo.x, rhi.x, rlo.y, rhi.y);
+    nodes[4 * i + 3] = make_float4(rlo.z, rhi.z, 0.0f, 0.0f);
 }
 
 // Sorted triangle records.  e0, e1 and N are computed with exactly the operations of
@@ -361,9 +361,10 @@ __global__ void __launch_bounds__(256) k_emit_tris(const rt_triangle* __restrict
     const V3 a = v3(t.a), b = v3(t.b), c = v3(t.c);
     const V3 e0 = b - a, e1 = c - a;
     const V3 N = cross(e0, e1);
-    geom[3 * s + 0] = make_float4(a.x, a.y, a.z, e0.x);
-    geom[3 * s + 1] = make_float4(e0.y, e0.z, e1.x, e1.y);
-    geom[3 * s + 2] = make_float4(e1.z, N.x, N.y, N.z);
+    geom[4 * s + 0] = make_float4(a.x, a.y, a.z, e0.x);
+    geom[4 * s + 1] = make_float4(e0.y, e0.z, e1.x, e1.y);
+    geom[4 * s + 2] = make_float4(e1.z, N.x, N.y, N.z);
+    geom[4 * s + 3] = make_float4(__int_as_float((int32_t)src), __int_as_float(t.materialIndex), 0.0f, 0.0f);
     shade[2 * s + 0] = make_float4(t.aTex[0], t.aTex[1], t.bTex[0], t.bTex[1]);
     shade[2 * s + 1] = make_float4(t.cTex[0], t.cTex[1], __int_as_float(t.materialIndex), __int_as_float((int32_t)src));
     orig[s] = (int32_t)src;

@@ -5,6 +5,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -99,6 +100,8 @@ constexpr int kMaxBounces = 4096;
 struct rt_ctx {
     rt_config cfg{};
     int sm_count = 148;
+    int extend_blocks_per_sm = 4;
+    int leaf_vote = 12, refill = 8;
     cudaStream_t own_stream = nullptr;
     cudaStream_t stream = nullptr;
     std::string err;
@@ -174,6 +177,9 @@ Launcher make_launcher(rt_ctx* ctx) {
     L.sm_count = ctx->sm_count;
     L.rng_mode = ctx->cfg.rng_mode;
     L.instrument = ctx->cfg.instrument != 0;
+    L.extend_grid = ctx->sm_count * ctx->extend_blocks_per_sm;
+    L.leaf_vote = ctx->leaf_vote;
+    L.refill = ctx->refill;
     L.kernel_launches = &ctx->kernel_launches;
     L.extend_launches = &ctx->extend_launches;
     L.ev_pool = ctx->events.data();
@@ -249,7 +255,7 @@ int prepare_image(rt_ctx* ctx, int W, int H) {
     CK(ctx->d_image.reserve((size_t)W * H * sizeof(float4)));
     CK(ctx->d_sum.reserve((size_t)W * H * 3 * sizeof(uint32_t)));
     CK(ctx->d_out.reserve((size_t)W * H * 3));
-    CK(ctx->d_counts.reserve((size_t)(kMaxBounces + 2) * sizeof(uint32_t)));
+    CK(ctx->d_counts.reserve((size_t)(kMaxBounces + 2) * 2 * sizeof(uint32_t)));
     CK(cudaMemsetAsync(ctx->d_image.p, 0, (size_t)W * H * sizeof(float4), ctx->stream));
     return RT_OK;
 }
@@ -444,6 +450,11 @@ int rt_create(rt_ctx** out, const rt_config* cfg) {
         return fail(nullptr, RT_ERR_CUDA, m);
     }
     ctx->stream = ctx->own_stream;
+    ctx->extend_blocks_per_sm = wf_extend_blocks_per_sm(cfg->instrument != 0);
+    // tuning knobs of the persistent traversal kernel (defaults chosen from ncu runs)
+    if (const char* e1 = getenv("RT_EXT_LEAF_VOTE")) ctx->leaf_vote = std::max(1, std::min(32, atoi(e1)));
+    if (const char* e2 = getenv("RT_EXT_REFILL")) ctx->refill = std::max(1, std::min(32, atoi(e2)));
+    if (const char* e3 = getenv("RT_EXT_BLOCKS_PER_SM")) ctx->extend_blocks_per_sm = std::max(1, std::min(32, atoi(e3)));
     if (ctx->d_stats.reserve(4 * sizeof(unsigned long long)) != cudaSuccess ||
         cudaMemsetAsync(ctx->d_stats.p, 0, 4 * sizeof(unsigned long long), ctx->stream) != cudaSuccess) {
         delete ctx;
@@ -487,7 +498,7 @@ int rt_set_stream(rt_ctx* ctx, void* cuda_stream) {
 int rt_scene_set_triangles(rt_ctx* ctx, const rt_triangle* tris, int64_t count) {
     GUARD();
     if (count < 0 || (count > 0 && !tris)) return fail(ctx, RT_ERR_INVALID, "rt_scene_set_triangles: bad argument");
-    if (count > (int64_t)kLeafFirstMask) return fail(ctx, RT_ERR_INVALID, "rt_scene_set_triangles: more than 2^27-1 triangles");
+    if (count > (int64_t)kLeafFirstMask - 8) return fail(ctx, RT_ERR_INVALID, "rt_scene_set_triangles: more than 2^27-9 triangles");
     CK(ctx->d_tris.reserve(std::max<size_t>((size_t)count, 1) * sizeof(rt_triangle)));
     if (count) CK(cudaMemcpyAsync(ctx->d_tris.p, tris, (size_t)count * sizeof(rt_triangle), cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));  // glBufferData semantics: the caller may free at once
@@ -555,7 +566,7 @@ int rt_scene_build(rt_ctx* ctx) {
     CK(ctx->d_node_depth.reserve(nn * sizeof(uint32_t)));
     CK(ctx->d_depth.reserve(sizeof(uint32_t)));
     CK(ctx->d_nodes.reserve(nn * 4 * sizeof(float4)));
-    CK(ctx->d_geom.reserve((size_t)n * 3 * sizeof(float4)));
+    CK(ctx->d_geom.reserve((size_t)n * 4 * sizeof(float4)));
     CK(ctx->d_shade.reserve((size_t)n * 2 * sizeof(float4)));
     CK(ctx->d_orig.reserve((size_t)n * sizeof(int32_t)));
     BuildArgs a;
@@ -734,11 +745,12 @@ int rt_scene_get_bvh(rt_ctx* ctx, rt_bvh_node* nodes, int64_t* node_count, int32
             const float4 n0 = raw[(size_t)i * 4], n1 = raw[(size_t)i * 4 + 1], n2 = raw[(size_t)i * 4 + 2], n3 = raw[(size_t)i * 4 + 3];
             rt_bvh_node& o = nodes[i];
             o.lo_x[0] = n0.x; o.hi_x[0] = n0.y; o.lo_y[0] = n0.z; o.hi_y[0] = n0.w;
-            o.lo_x[1] = n1.x; o.hi_x[1] = n1.y; o.lo_y[1] = n1.z; o.hi_y[1] = n1.w;
-            o.lo_z[0] = n2.x; o.hi_z[0] = n2.y; o.lo_z[1] = n2.z; o.hi_z[1] = n2.w;
+            o.lo_z[0] = n1.x; o.hi_z[0] = n1.y;
+            o.lo_x[1] = n2.x; o.hi_x[1] = n2.y; o.lo_y[1] = n2.z; o.hi_y[1] = n2.w;
+            o.lo_z[1] = n3.x; o.hi_z[1] = n3.y;
             int32_t c[2];
-            memcpy(&c[0], &n3.x, 4);
-            memcpy(&c[1], &n3.y, 4);
+            memcpy(&c[0], &n1.z, 4);
+            memcpy(&c[1], &n1.w, 4);
             for (int k = 0; k < 2; k++) {
                 if (c[k] >= 0) {
                     o.child[k] = c[k];

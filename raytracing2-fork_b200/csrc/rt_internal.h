@@ -24,7 +24,7 @@ struct BuildArgs {
     uint32_t* nodeDepth;      // n-1 (height of the subtree under each inner node)
     uint32_t* maxDepth;       // 1
     float4* nodes;            // 4*(n-1)   (output)
-    float4* geom;             // 3*n       (output)
+    float4* geom;             // 4*n       (output)
     float4* shade;            // 2*n       (output)
     int32_t* orig;            // n         (output)
 };
@@ -54,7 +54,8 @@ struct WaveBuffers {
     float4* contrib;      // radiance of each (lane, pixel) slot of the batch
     float4* accum;        // running sum per local pixel (xyz) 
     uint32_t* pix_rng;    // RT_RNG_REF_PCG: the per-pixel stream state carried across samples
-    uint32_t* counts;     // counts[b] = live paths entering bounce b   (maxBounce + 2 entries)
+    uint32_t* counts;     // counts[b] = live paths entering bounce b (maxBounce + 2 entries), followed by
+                          // the same number of k_extend work cursors
     unsigned long long* stats;  // [0] segments [1] paths [2] node visits [3] tri tests
     float4* image;        // W*H RGBA32F, bottom-up (the reference's image binding 0)
     uint32_t* frame_sum;  // W*H*3 sums of the 8-bit frames, bottom-up
@@ -66,6 +67,9 @@ struct Launcher {
     int sm_count;
     int rng_mode;
     bool instrument;
+    int extend_grid;   // persistent k_extend grid: SMs x resident blocks per SM
+    int leaf_vote;     // k_extend: leaf step when this many lanes wait at a leaf
+    int refill;        // k_extend: refill when this many lanes are idle
     uint64_t* kernel_launches;
     uint64_t* extend_launches;
     // optional per-class device timing
@@ -76,6 +80,7 @@ struct Launcher {
     bool timing;
 };
 
+int wf_extend_blocks_per_sm(bool instrument);
 cudaError_t wf_clear_accum(const Launcher& L, const WaveBuffers& wb, int local_pixels);
 cudaError_t wf_seed_pixels(const Launcher& L, const SceneView& sc, const WaveBuffers& wb, const FrameParams& fp);
 cudaError_t wf_render_batch(const Launcher& L, const SceneView& sc, const WaveBuffers& wb, const FrameParams& fp);

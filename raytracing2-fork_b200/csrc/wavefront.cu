@@ -141,7 +141,7 @@ __device__ __forceinline__ bool black_checker(V3 p, float scale) {  // S:524-527
     return m == 0.0f;
 }
 __device__ __forceinline__ V3 tri_normal(const SceneView& sc, int32_t slot) {  // S:331
-    const float4 g2 = __ldg(&sc.tri_geom[3 * slot + 2]);
+    const float4 g2 = __ldg(&sc.tri_geom[4 * slot + 2]);
     return normalize(v3(g2.y, g2.z, g2.w));
 }
 
@@ -202,7 +202,7 @@ __global__ void __launch_bounds__(kBlock) k_raygen(const __grid_constant__ Frame
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i == 0) {
         counts[0] = (uint32_t)n;
-        for (int k = 1; k < ncounts; k++) counts[k] = 0u;
+        for (int k = 1; k < 2 * ncounts; k++) counts[k] = 0u;  // live counts, then the extend cursors
         atomicAdd(&stats[1], (unsigned long long)n);
     }
     if (i >= n) return;
@@ -222,26 +222,200 @@ __global__ void __launch_bounds__(kBlock) k_raygen(const __grid_constant__ Frame
     contrib[i] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
 }
 
+// ---------------------------------------------------------------------------------------------- k_extend
+// Persistent warps.  Every lane owns at most one ray; finished lanes are refilled from the queue
+// through a device-side cursor (one atomicAdd per refill, claimed by the first idle lane), so a warp
+// never waits for its slowest ray.  Each iteration the warp VOTES on what to execute: a leaf step
+// (exact Möller–Trumbore, compute.glsl:302-340) when at least `leafVote` lanes are parked at a leaf or
+// nobody can take a node step, otherwise a node step (two slab tests) — both are executed under a
+// warp-uniform branch, so the instruction stream never serialises node and triangle code inside one
+// iteration.  ncu on the v1 kernel (one thread per ray, per-lane if/else) showed 6.85 of 32 lanes
+// active per instruction; this structure is what that measurement asked for
+// (profiles/r1_v1_extend_ncu_full.md).
+//
+// The closest-hit rule (min dst, then lowest original index) makes the result independent of the
+// order in which lanes, nodes and triangles are visited, so the restructuring changes no bit.
+constexpr int kExtBlock = 128;
+constexpr int32_t kPop = (int32_t)0x80000000;       // lane state: take the next subtree from the stack
+constexpr int32_t kIdle = (int32_t)0x80000001;      // lane state: no ray
+struct ExtendTune {
+    int leafVote;  // leaf step when >= this many lanes wait at a leaf
+    int refill;    // refill when >= this many lanes are idle
+};
+
+// One node step for a lane at an inner node: two slab tests, then a branch-free choice of the next
+// state (near child / push far child / pop).  v2's if/else ladder here ran at 3-8 active lanes
+// (profiles/r1_v2_extend_ncu_full.md); selects and one predicated store keep the warp converged.
+struct RayRegs {
+    V3 o, d;
+    float idx, idy, idz;
+    float bestT;
+};
+// Traversal stack: the first kShStack entries of every lane live in shared memory laid out
+// [level][thread], so a warp-wide push or pop is conflict-free (one bank pair per lane) whatever
+// the lanes' depths are; in local memory the same access scatters over up to 32 lines and costs up
+// to 32 L1TEX wavefronts.  Deeper entries (rare: LBVH depth is ~2 log2 n) overflow to local memory.
+constexpr int kShStack = 16;
+struct Stack {
+    int2* sh;         // &shared[0][threadIdx.x]; stride kExtBlock
+    int32_t* ovNode;  // local overflow
+    float* ovT;
+    __device__ __forceinline__ void push(int sp, int32_t c, float t) {
+        if (sp < kShStack) sh[sp * kExtBlock] = make_int2(c, __float_as_int(t));
+        else { ovNode[sp - kShStack] = c; ovT[sp - kShStack] = t; }
+    }
+    __device__ __forceinline__ void get(int sp, int32_t& c, float& t) const {
+        if (sp < kShStack) { const int2 e = sh[sp * kExtBlock]; c = e.x; t = __int_as_float(e.y); }
+        else { c = ovNode[sp - kShStack]; t = ovT[sp - kShStack]; }
+    }
+};
+__device__ __forceinline__ void node_step(const SceneView& sc, const RayRegs& r, int32_t& node, int& sp, Stack& st) {
+    const float kWiden = 1.000001f;
+    float nl[8], nr[8];
+    ldg256(sc.nodes + 4 * node, nl);
+    ldg256(sc.nodes + 4 * node + 2, nr);
+    const float lx0 = (nl[0] - r.o.x) * r.idx, lx1 = (nl[1] - r.o.x) * r.idx;
+    const float ly0 = (nl[2] - r.o.y) * r.idy, ly1 = (nl[3] - r.o.y) * r.idy;
+    const float lz0 = (nl[4] - r.o.z) * r.idz, lz1 = (nl[5] - r.o.z) * r.idz;
+    const float rx0 = (nr[0] - r.o.x) * r.idx, rx1 = (nr[1] - r.o.x) * r.idx;
+    const float ry0 = (nr[2] - r.o.y) * r.idy, ry1 = (nr[3] - r.o.y) * r.idy;
+    const float rz0 = (nr[4] - r.o.z) * r.idz, rz1 = (nr[5] - r.o.z) * r.idz;
+    const float lNear = fmaxf(fmaxf(fminf(lx0, lx1), fminf(ly0, ly1)), fmaxf(fminf(lz0, lz1), 0.0f));
+    const float rNear = fmaxf(fmaxf(fminf(rx0, rx1), fminf(ry0, ry1)), fmaxf(fminf(rz0, rz1), 0.0f));
+    const float lFar = fminf(fminf(fmaxf(lx0, lx1), fmaxf(ly0, ly1)), fminf(fmaxf(lz0, lz1), r.bestT)) * kWiden;
+    const float rFar = fminf(fminf(fmaxf(rx0, rx1), fmaxf(ry0, ry1)), fminf(fmaxf(rz0, rz1), r.bestT)) * kWiden;
+    const bool hitL = lNear <= lFar;
+    const bool hitR = rNear <= rFar;
+    const int32_t cl = __float_as_int(nl[6]), cr = __float_as_int(nl[7]);
+    const bool both = hitL && hitR;
+    const bool goLeft = hitL && (!hitR || lNear <= rNear);
+    const int32_t nearC = goLeft ? cl : cr;
+    if (both) st.push(sp, goLeft ? cr : cl, goLeft ? rNear : lNear);
+    sp += both ? 1 : 0;
+    node = (hitL || hitR) ? nearC : kPop;
+}
+
 template <bool COUNT>
-__global__ void __launch_bounds__(kBlock) k_extend(const __grid_constant__ SceneView sc, PathArrays cur,
-                                                   float4* __restrict__ hit, const uint32_t* __restrict__ count,
-                                                   unsigned long long* __restrict__ stats) {
+__global__ void __launch_bounds__(kExtBlock) k_extend(const __grid_constant__ SceneView sc, PathArrays cur,
+                                                      float4* __restrict__ hit, const uint32_t* __restrict__ count,
+                                                      uint32_t* __restrict__ cursor, ExtendTune tune,
+                                                      unsigned long long* __restrict__ stats) {
     const uint32_t n = *count;
     if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&stats[0], (unsigned long long)n);
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t ltMask = (1u << lane) - 1u;
+    constexpr uint32_t FULL = 0xffffffffu;
+    const float kWiden = 1.000001f;
+
+    __shared__ int2 shStack[kShStack][kExtBlock];
+    int32_t ovNode[kStackSize - kShStack];
+    float ovT[kStackSize - kShStack];
+    Stack st{&shStack[0][threadIdx.x], ovNode, ovT};
+    bool exhausted = (n == 0u) || sc.num_tris <= 0;
+    uint32_t ray = 0;
+    RayRegs r;
+    r.o = v3(0, 0, 0); r.d = v3(0, 0, 1); r.idx = r.idy = r.idz = 0.0f; r.bestT = kMissT;
+    float bestU = 0, bestV = 0;
+    int32_t bestSlot = -1, bestOrig = 0x7fffffff;
+    int32_t node = kIdle;
+    int sp = 0;
     uint32_t visits = 0, tests = 0;
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        const float4 a = cur.od0[i];
-        const float4 b = cur.od1[i];
-        const HitRec h = closest_hit<COUNT>(sc, v3(a.x, a.y, a.z), v3(a.w, b.x, b.y), visits, tests);
-        hit[i] = make_float4(h.t, h.u, h.v, __int_as_float(h.slot));
+
+    if (sc.num_tris <= 0) {  // empty scene: every ray misses
+        for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+            hit[i] = make_float4(kMissT, 0.0f, 0.0f, __int_as_float(-1));
+    }
+
+    for (;;) {
+        // ---- pop phase: lanes that finished a subtree take the next one that can still hold a hit
+        if (node == kPop) {
+            if (sp == 0) {
+                hit[ray] = make_float4(r.bestT, bestU, bestV, __int_as_float(bestSlot));
+                node = kIdle;
+            } else {
+                --sp;
+                float tn;
+                int32_t c;
+                st.get(sp, c, tn);
+                if (tn <= r.bestT * kWiden) node = c;
+            }
+        }
+        // ---- refill idle lanes from the queue
+        uint32_t idle = __ballot_sync(FULL, node == kIdle);
+        if (!exhausted && ((int)__popc(idle) >= tune.refill || idle == FULL)) {
+            uint32_t base = 0;
+            const int leader = __ffs(idle) - 1;
+            const uint32_t want = __popc(idle);
+            if ((int)lane == leader) base = atomicAdd(cursor, want);
+            base = __shfl_sync(FULL, base, leader);
+            if (node == kIdle) {
+                const uint32_t i = base + __popc(idle & ltMask);
+                if (i < n) {
+                    const float4 a = cur.od0[i];
+                    const float4 b = cur.od1[i];
+                    ray = i;
+                    r.o = v3(a.x, a.y, a.z);
+                    r.d = v3(a.w, b.x, b.y);
+                    // IEEE division: a zero component gives +-inf; NaNs (inf*0) drop out of fminf/fmaxf
+                    r.idx = 1.0f / r.d.x;
+                    r.idy = 1.0f / r.d.y;
+                    r.idz = 1.0f / r.d.z;
+                    r.bestT = kMissT; bestU = 0.0f; bestV = 0.0f; bestSlot = -1; bestOrig = 0x7fffffff;
+                    sp = 0;
+                    node = sc.root_is_leaf ? pack_leaf(0, sc.num_tris) : 0;
+                }
+            }
+            if (base + want >= n) exhausted = true;
+            idle = __ballot_sync(FULL, node == kIdle);
+        }
+        if (idle == FULL) {
+            if (exhausted) break;
+            continue;
+        }
+        // ---- vote: leaf step or node steps (warp-uniform branch)
+        const uint32_t leafM = __ballot_sync(FULL, node < 0 && node != kPop && node != kIdle);
+        const uint32_t nodeM = __ballot_sync(FULL, node >= 0);
+        if ((int)__popc(leafM) >= tune.leafVote || nodeM == 0u) {
+            if (node < 0 && node != kPop && node != kIdle) {
+                const int32_t packed = ~node;
+                const int32_t first = packed & kLeafFirstMask;
+                const int32_t cnt = (packed >> kLeafCountShift) + 1;
+                for (int32_t s = first; s < first + cnt; s++) {
+                    float g[8], h[8];
+                    ldg256(sc.tri_geom + 4 * s, g);
+                    ldg256(sc.tri_geom + 4 * s + 2, h);
+                    if (COUNT) tests++;
+                    float dst, u, v;
+                    if (ray_triangle(r.o, r.d, v3(g[0], g[1], g[2]), v3(g[3], g[4], g[5]), v3(g[6], g[7], h[0]),
+                                     v3(h[1], h[2], h[3]), dst, u, v)) {
+                        if (dst <= r.bestT && dst < kMissT) {
+                            const int32_t orig = __float_as_int(h[4]);
+                            if (dst < r.bestT || orig < bestOrig) {
+                                r.bestT = dst; bestU = u; bestV = v; bestSlot = s; bestOrig = orig;
+                            }
+                        }
+                    }
+                }
+                node = kPop;
+            }
+        } else {
+            if (node >= 0) {
+                if (COUNT) visits++;
+                node_step(sc, r, node, sp, st);
+            }
+            if (node >= 0) {  // a second step before the next vote halves the voting overhead per step
+                if (COUNT) visits++;
+                node_step(sc, r, node, sp, st);
+            }
+        }
     }
     if (COUNT) {
 #pragma unroll
         for (int off = 16; off > 0; off >>= 1) {
-            visits += __shfl_xor_sync(0xffffffffu, visits, off);
-            tests += __shfl_xor_sync(0xffffffffu, tests, off);
+            visits += __shfl_xor_sync(FULL, visits, off);
+            tests += __shfl_xor_sync(FULL, tests, off);
         }
-        if ((threadIdx.x & 31) == 0) {
+        if (lane == 0) {
             atomicAdd(&stats[2], (unsigned long long)visits);
             atomicAdd(&stats[3], (unsigned long long)tests);
         }
@@ -608,6 +782,14 @@ struct Timed {
     }
 };
 
+int wf_extend_blocks_per_sm(bool instrument) {
+    int nb = 0;
+    cudaError_t e = instrument
+        ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_extend<true>, kExtBlock, 0)
+        : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_extend<false>, kExtBlock, 0);
+    return e == cudaSuccess && nb > 0 ? nb : 4;
+}
+
 cudaError_t wf_clear_accum(const Launcher& L, const WaveBuffers& wb, int local_pixels) {
     k_clear_accum<<<nblocks(local_pixels), kBlock, 0, L.st>>>(wb.accum, local_pixels);
     (*L.kernel_launches)++;
@@ -632,17 +814,20 @@ cudaError_t wf_render_batch(const Launcher& L, const SceneView& sc, const WaveBu
             k_raygen<1><<<nblocks(n), kBlock, 0, L.st>>>(fp, wb.cur, wb.contrib, wb.pix_rng, wb.counts, ncounts, wb.stats);
         (*L.kernel_launches)++;
     }
-    // fixed-size grids that stride over the live count read on the device: no host round trip per bounce
+    // fixed-size grids that read the live count on the device: no host round trip per bounce
     const int grid = (int)((n + kBlock - 1) / kBlock < (long long)L.sm_count * 8 ? (n + kBlock - 1) / kBlock
                                                                                 : (long long)L.sm_count * 8);
+    const int extGrid = L.extend_grid;
+    uint32_t* cursors = wb.counts + ncounts;
+    ExtendTune tune{L.leaf_vote, L.refill};
     PathArrays a = wb.cur, b = wb.next;
     for (int bounce = 0; bounce < maxB; bounce++) {
         {
             Timed t(L, 0);
             if (L.instrument)
-                k_extend<true><<<grid, kBlock, 0, L.st>>>(sc, a, wb.hit, wb.counts + bounce, wb.stats);
+                k_extend<true><<<extGrid, kExtBlock, 0, L.st>>>(sc, a, wb.hit, wb.counts + bounce, cursors + bounce, tune, wb.stats);
             else
-                k_extend<false><<<grid, kBlock, 0, L.st>>>(sc, a, wb.hit, wb.counts + bounce, wb.stats);
+                k_extend<false><<<extGrid, kExtBlock, 0, L.st>>>(sc, a, wb.hit, wb.counts + bounce, cursors + bounce, tune, wb.stats);
             (*L.kernel_launches)++;
             (*L.extend_launches)++;
         }
