@@ -9,7 +9,7 @@
 //                  scatter with warp match-any ranking (k_scatter)
 //   k_hierarchy    Karras 2012: one thread per inner node finds its range and split
 //   k_refit        bottom-up AABB union with one atomic flag per inner node
-//   k_emit_nodes   64-byte nodes with both child boxes in the parent
+//   k_emit_nodes   32-byte nodes: both child boxes in the parent, 16-bit planes rounded outward
 //   k_emit_tris    sorted triangle records: (a, e0, e1, N, orig, material) | (uvs, material, orig)
 // Everything is deterministic (stable sort, min/max are order independent), so every GPU of a
 // multi-GPU job builds the identical tree.
@@ -331,9 +331,22 @@ __global__ void __launch_bounds__(256) k_refit(const rt_triangle* __restrict__ t
     atomicMax(maxDepth, depth);
 }
 
+// Grid of the quantised boxes: 65535 cells over the scene box padded by 2 leaf pads per side.
+// grid[0..2] = world position of coordinate 0, grid[3..5] = cells per world unit.
+__global__ void k_grid(const uint32_t* __restrict__ bounds, float* __restrict__ grid) {
+    const int k = threadIdx.x;
+    if (k >= 3) return;
+    float ext = 0.0f;
+    for (int a = 0; a < 3; a++) ext = fmaxf(ext, ord2f(bounds[9 + a]) - ord2f(bounds[6 + a]));
+    const float pad = 2.0f * fmaxf(1e-4f, 2e-6f * ext);
+    const float lo = ord2f(bounds[6 + k]) - pad, hi = ord2f(bounds[9 + k]) + pad;
+    grid[k] = lo;
+    grid[3 + k] = 65535.0f / fmaxf(hi - lo, 1e-30f);
+}
+
 __global__ void __launch_bounds__(256) k_emit_nodes(int n, const int32_t* __restrict__ children,
                                                     const float4* __restrict__ boxes,
-                                                    float4* __restrict__ nodes) {
+                                                    const float* __restrict__ grid, uint4* __restrict__ nodes) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n - 1) return;
     const int32_t cl = children[2 * i], cr = children[2 * i + 1];
@@ -342,10 +355,26 @@ __global__ void __launch_bounds__(256) k_emit_nodes(int n, const int32_t* __rest
     const float4 rlo = boxes[2 * er], rhi = boxes[2 * er + 1];
     const int32_t pl = cl >= 0 ? cl : pack_leaf(~cl, 1);
     const int32_t pr = cr >= 0 ? cr : pack_leaf(~cr, 1);
-    nodes[4 * i + 0] = make_float4(llo.x, lhi.x, llo.y, lhi.y);
-    nodes[4 * i + 1] = make_float4(llo.z, lhi.z, __int_as_float(pl), __int_as_float(pr));
-    nodes[4 * i + 2] = make_float4(rlo.x, rhi.x, rlo.y, rhi.y);
-    nodes[4 * i + 3] = make_float4(rlo.z, rhi.z, 0.0f, 0.0f);
+    // outward rounding with a 1e-3 cell guard band against the rounding of the scaling itself
+    auto qlo = [&](float v, int k) {
+        const float c = floorf((v - grid[k]) * grid[3 + k] - 1e-3f);
+        return (uint32_t)fminf(fmaxf(c, 0.0f), 65535.0f);
+    };
+    auto qhi = [&](float v, int k) {
+        const float c = ceilf((v - grid[k]) * grid[3 + k] + 1e-3f);
+        return (uint32_t)fminf(fmaxf(c, 0.0f), 65535.0f);
+    };
+    uint4 a, b;
+    a.x = qlo(llo.x, 0) | (qhi(lhi.x, 0) << 16);
+    a.y = qlo(llo.y, 1) | (qhi(lhi.y, 1) << 16);
+    a.z = qlo(llo.z, 2) | (qhi(lhi.z, 2) << 16);
+    a.w = qlo(rlo.x, 0) | (qhi(rhi.x, 0) << 16);
+    b.x = qlo(rlo.y, 1) | (qhi(rhi.y, 1) << 16);
+    b.y = qlo(rlo.z, 2) | (qhi(rhi.z, 2) << 16);
+    b.z = (uint32_t)pl;
+    b.w = (uint32_t)pr;
+    nodes[2 * i + 0] = a;
+    nodes[2 * i + 1] = b;
 }
 
 // Sorted triangle records.  e0, e1 and N are computed with exactly the operations of
@@ -405,7 +434,8 @@ cudaError_t build_lbvh(const BuildArgs& a, cudaStream_t st, uint64_t* launches) 
     }
     k_refit<<<nb(n, 256), 256, 0, st>>>(a.tris, a.vals[0], n, a.bounds, a.children, a.parent, a.boxes, a.flags,
                                         a.nodeDepth, a.maxDepth); L++;
-    if (n >= 2) { k_emit_nodes<<<nb(n - 1, 256), 256, 0, st>>>(n, a.children, a.boxes, a.nodes); L++; }
+    k_grid<<<1, 32, 0, st>>>(a.bounds, a.grid); L++;
+    if (n >= 2) { k_emit_nodes<<<nb(n - 1, 256), 256, 0, st>>>(n, a.children, a.boxes, a.grid, a.nodes); L++; }
     k_emit_tris<<<nb(n, 256), 256, 0, st>>>(a.tris, a.vals[0], n, a.geom, a.shade, a.orig); L++;
     if (launches) *launches += L;
     return cudaGetLastError();

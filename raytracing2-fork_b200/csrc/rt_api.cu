@@ -118,7 +118,8 @@ struct rt_ctx {
     int tex_w[RT_MAX_TEXTURES] = {0}, tex_h[RT_MAX_TEXTURES] = {0}, tex_ch[RT_MAX_TEXTURES] = {0};
     // build scratch + outputs
     DevBuf d_centroid, d_bounds, d_keys[2], d_vals[2], d_hist, d_children, d_parent, d_boxes, d_flags, d_depth, d_node_depth;
-    DevBuf d_nodes, d_geom, d_shade, d_orig;
+    DevBuf d_nodes, d_geom, d_shade, d_orig, d_grid;
+    float grid[6] = {0, 0, 0, 1, 1, 1};
     // wavefront
     DevBuf d_path[6], d_hit, d_contrib, d_accum, d_pixrng, d_counts, d_stats, d_image, d_sum, d_out, d_rows;
     DevBuf d_stage, d_compact;  // tile-split gather
@@ -193,7 +194,11 @@ Launcher make_launcher(rt_ctx* ctx) {
 SceneView make_view(rt_ctx* ctx) {
     SceneView v;
     memset(&v, 0, sizeof v);
-    v.nodes = ctx->d_nodes.as<float4>();
+    v.nodes = ctx->d_nodes.as<uint4>();
+    for (int k = 0; k < 3; k++) {
+        v.grid_lo[k] = ctx->grid[k];
+        v.grid_inv[k] = ctx->grid[3 + k];
+    }
     v.tri_geom = ctx->d_geom.as<float4>();
     v.tri_shade = ctx->d_shade.as<float4>();
     v.tri_orig = ctx->d_orig.as<int32_t>();
@@ -476,7 +481,7 @@ void rt_destroy(rt_ctx* ctx) {
     if (ctx->comm && nccl().ok) nccl().CommDestroy(ctx->comm);
     DevBuf* all[] = {&ctx->d_tris, &ctx->d_mats, &ctx->d_centroid, &ctx->d_bounds, &ctx->d_keys[0], &ctx->d_keys[1],
                      &ctx->d_vals[0], &ctx->d_vals[1], &ctx->d_hist, &ctx->d_children, &ctx->d_parent, &ctx->d_boxes,
-                     &ctx->d_flags, &ctx->d_depth, &ctx->d_node_depth, &ctx->d_nodes, &ctx->d_geom, &ctx->d_shade, &ctx->d_orig, &ctx->d_hit,
+                     &ctx->d_flags, &ctx->d_depth, &ctx->d_node_depth, &ctx->d_nodes, &ctx->d_grid, &ctx->d_geom, &ctx->d_shade, &ctx->d_orig, &ctx->d_hit,
                      &ctx->d_contrib, &ctx->d_accum, &ctx->d_pixrng, &ctx->d_counts, &ctx->d_stats, &ctx->d_image,
                      &ctx->d_sum, &ctx->d_out, &ctx->d_rows, &ctx->d_stage, &ctx->d_compact};
     for (DevBuf* b : all) b->release();
@@ -565,7 +570,8 @@ int rt_scene_build(rt_ctx* ctx) {
     CK(ctx->d_flags.reserve(nn * sizeof(uint32_t)));
     CK(ctx->d_node_depth.reserve(nn * sizeof(uint32_t)));
     CK(ctx->d_depth.reserve(sizeof(uint32_t)));
-    CK(ctx->d_nodes.reserve(nn * 4 * sizeof(float4)));
+    CK(ctx->d_nodes.reserve(nn * 2 * sizeof(uint4)));
+    CK(ctx->d_grid.reserve(6 * sizeof(float)));
     CK(ctx->d_geom.reserve((size_t)n * 4 * sizeof(float4)));
     CK(ctx->d_shade.reserve((size_t)n * 2 * sizeof(float4)));
     CK(ctx->d_orig.reserve((size_t)n * sizeof(int32_t)));
@@ -585,7 +591,8 @@ int rt_scene_build(rt_ctx* ctx) {
     a.flags = ctx->d_flags.as<uint32_t>();
     a.nodeDepth = ctx->d_node_depth.as<uint32_t>();
     a.maxDepth = ctx->d_depth.as<uint32_t>();
-    a.nodes = ctx->d_nodes.as<float4>();
+    a.nodes = ctx->d_nodes.as<uint4>();
+    a.grid = ctx->d_grid.as<float>();
     a.geom = ctx->d_geom.as<float4>();
     a.shade = ctx->d_shade.as<float4>();
     a.orig = ctx->d_orig.as<int32_t>();
@@ -597,6 +604,7 @@ int rt_scene_build(rt_ctx* ctx) {
     CK(cudaEventRecord(e1, ctx->stream));
     uint32_t depth = 0;
     CK(cudaMemcpyAsync(&depth, ctx->d_depth.p, sizeof depth, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->grid, ctx->d_grid.p, sizeof ctx->grid, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     float ms = 0.0f;
     cudaEventElapsedTime(&ms, e0, e1);
@@ -739,18 +747,20 @@ int rt_scene_get_bvh(rt_ctx* ctx, rt_bvh_node* nodes, int64_t* node_count, int32
     if (tri_count) *tri_count = n;
     CK(cudaStreamSynchronize(ctx->stream));
     if (nodes && nn > 0) {
-        std::vector<float4> raw((size_t)nn * 4);
-        CK(cudaMemcpy(raw.data(), ctx->d_nodes.p, raw.size() * sizeof(float4), cudaMemcpyDeviceToHost));
+        std::vector<uint4> raw((size_t)nn * 2);
+        CK(cudaMemcpy(raw.data(), ctx->d_nodes.p, raw.size() * sizeof(uint4), cudaMemcpyDeviceToHost));
+        const float* G = ctx->grid;
+        auto deq = [&](uint32_t q, int k) { return G[k] + (float)q / G[3 + k]; };
         for (int64_t i = 0; i < nn; i++) {
-            const float4 n0 = raw[(size_t)i * 4], n1 = raw[(size_t)i * 4 + 1], n2 = raw[(size_t)i * 4 + 2], n3 = raw[(size_t)i * 4 + 3];
+            const uint4 a = raw[(size_t)i * 2], b = raw[(size_t)i * 2 + 1];
             rt_bvh_node& o = nodes[i];
-            o.lo_x[0] = n0.x; o.hi_x[0] = n0.y; o.lo_y[0] = n0.z; o.hi_y[0] = n0.w;
-            o.lo_z[0] = n1.x; o.hi_z[0] = n1.y;
-            o.lo_x[1] = n2.x; o.hi_x[1] = n2.y; o.lo_y[1] = n2.z; o.hi_y[1] = n2.w;
-            o.lo_z[1] = n3.x; o.hi_z[1] = n3.y;
-            int32_t c[2];
-            memcpy(&c[0], &n1.z, 4);
-            memcpy(&c[1], &n1.w, 4);
+            o.lo_x[0] = deq(a.x & 0xffffu, 0); o.hi_x[0] = deq(a.x >> 16, 0);
+            o.lo_y[0] = deq(a.y & 0xffffu, 1); o.hi_y[0] = deq(a.y >> 16, 1);
+            o.lo_z[0] = deq(a.z & 0xffffu, 2); o.hi_z[0] = deq(a.z >> 16, 2);
+            o.lo_x[1] = deq(a.w & 0xffffu, 0); o.hi_x[1] = deq(a.w >> 16, 0);
+            o.lo_y[1] = deq(b.x & 0xffffu, 1); o.hi_y[1] = deq(b.x >> 16, 1);
+            o.lo_z[1] = deq(b.y & 0xffffu, 2); o.hi_z[1] = deq(b.y >> 16, 2);
+            const int32_t c[2] = {(int32_t)b.z, (int32_t)b.w};
             for (int k = 0; k < 2; k++) {
                 if (c[k] >= 0) {
                     o.child[k] = c[k];
@@ -799,7 +809,7 @@ int rt_get_counters(rt_ctx* ctx, rt_counters* out) {
     out->shade_ms = ctx->shade_ms_acc;
     out->build_ms = ctx->build_ms;
     out->bvh_nodes = ctx->n_tris >= 2 ? (uint64_t)ctx->n_tris - 1 : 0;
-    out->bvh_bytes = out->bvh_nodes * 64 + (uint64_t)ctx->n_tris * 48;
+    out->bvh_bytes = out->bvh_nodes * 32 + (uint64_t)ctx->n_tris * 48;
     out->bvh_depth = ctx->bvh_depth;
     return RT_OK;
 }

@@ -23,7 +23,8 @@ struct BuildArgs {
     uint32_t* flags;          // n-1
     uint32_t* nodeDepth;      // n-1 (height of the subtree under each inner node)
     uint32_t* maxDepth;       // 1
-    float4* nodes;            // 4*(n-1)   (output)
+    float* grid;              // 6: quantisation grid (output)
+    uint4* nodes;             // 2*(n-1)   (output)
     float4* geom;             // 4*n       (output)
     float4* shade;            // 2*n       (output)
     int32_t* orig;            // n         (output)

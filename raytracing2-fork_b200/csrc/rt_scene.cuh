@@ -1,27 +1,29 @@
 // rt_scene.cuh — device-side scene layout and the closest-hit traversal shared by every kernel.
 //
-// HBM layout, all arrays 32-byte aligned and read with 256-bit loads (LDG.E.256 on
-// sm_100a).  ncu showed the traversal kernel bound by L1TEX wavefronts (l1tex data pipe 89 % busy):
-// a gather where every lane reads its own node costs one wavefront per lane per load instruction,
-// so the layouts minimise the NUMBER OF LOAD INSTRUCTIONS per visit: a node is two 32-byte loads,
-// a triangle two.
-//   nodes    : 64 B per inner node, BOTH child boxes in the parent (the reference re-reads the parent
-//              and then two 48-byte children: 144 B per visit, compute.glsl:425,443-444)
-//                v8 #0 = (L.lo.x, L.hi.x, L.lo.y, L.hi.y, L.lo.z, L.hi.z, left, right)   [ints as bits]
-//                v8 #1 = (R.lo.x, R.hi.x, R.lo.y, R.hi.y, R.lo.z, R.hi.z, 0, 0)
-//              child >= 0: inner node index; child < 0: leaf, ~child = first | (count-1) << 27
-//   tri_geom : 64 B per sorted triangle = a, e0 = b-a, e1 = c-a, N = cross(e0,e1) (48 B, precomputed
-//              with the very operations compute.glsl:307-309 performs per test, so every bit of
-//              dst,u,v is unchanged), then original index, material index, 2 pad words
+// HBM layout.  ncu showed the traversal kernel bound by the L1TEX data pipe
+// (l1tex__data_pipe_lsu_wavefronts 89-95 % of peak): a gather where every lane reads its own node is
+// served at ~16 bytes per lane per wavefront, so the only lever is BYTES PER VISIT.
+//   nodes    : 32 B per inner node = ONE 256-bit load (LDG.E.256 on sm_100a).  Both child boxes
+//              live in the parent, quantised to 16 bits per plane on a global grid over the padded
+//              scene box and rounded OUTWARD (the boxes only prune, so a larger box is always
+//              safe; triangle tests stay exact binary32):
+//                w0..w2 = left  child (lo.x | hi.x << 16, lo.y | hi.y << 16, lo.z | hi.z << 16)
+//                w3..w5 = right child, w6 = left, w7 = right
+//              child >= 0: inner node index; child < 0: leaf, ~child = first | (count-1) << 27.
+//              (The reference re-reads the 48-byte parent and then two 48-byte children per visit:
+//              144 B, compute.glsl:425,443-444.)
+//   tri_geom : 64 B stride per sorted triangle; traversal reads the first 48 B = a, e0 = b-a,
+//              e1 = c-a, N = cross(e0,e1), precomputed with the very operations
+//              compute.glsl:307-309 performs per test, so every bit of dst,u,v is unchanged
 //   tri_shade: 32 B per sorted triangle = aTex,bTex,cTex, materialIndex, original index
-//   tri_orig : 4 B per sorted triangle, the index in the caller's array (reported id)
+//   tri_orig : 4 B per sorted triangle, the index in the caller's array (tie-break + reported id)
 #pragma once
 #include "rt_math.cuh"
 
 namespace rt {
 
 struct SceneView {
-    const float4* __restrict__ nodes;      // 4 per inner node (64 B, 32-byte aligned)
+    const uint4* __restrict__ nodes;       // 2 per inner node (32 B, 32-byte aligned)
     const float4* __restrict__ tri_geom;   // 4 per sorted triangle (64 B, 32-byte aligned)
     const float4* __restrict__ tri_shade;  // 2 per sorted triangle
     const int32_t* __restrict__ tri_orig;
@@ -31,6 +33,8 @@ struct SceneView {
     int32_t num_tris;
     int32_t num_materials;
     int32_t root_is_leaf;  // scenes with a single triangle have no inner node
+    float grid_lo[3];      // world position of quantised coordinate 0
+    float grid_inv[3];     // cells per world unit (65535 cells span the padded scene box)
 };
 
 struct HitRec {
@@ -43,6 +47,77 @@ constexpr int kStackSize = 64;
 
 // 256-bit read-only global load (sm_100a: LDG.E.ENL2.256.CONSTANT): one instruction, one L1TEX
 // wavefront per lane for 32 bytes, where four 128-bit loads of a 64-byte record would cost four.
+__device__ __forceinline__ void ldg256u(const void* p, uint32_t (&v)[8]) {
+    asm volatile("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+                 : "l"(p));
+}
+// exact uint16 -> float.  RT_DEQ_I2F: one I2F.U16 per plane (reads the half register directly, XU
+// pipe); otherwise splice into the mantissa of 2^23 and subtract 2^23 (LOP3 + FADD, ALU/FMA pipes).
+#ifndef RT_DEQ_I2F
+#define RT_DEQ_I2F 1
+#endif
+#if RT_DEQ_I2F
+__device__ __forceinline__ float q_lo(uint32_t w) { return (float)(uint16_t)(w & 0xffffu); }
+__device__ __forceinline__ float q_hi(uint32_t w) { return (float)(uint16_t)(w >> 16); }
+#else
+__device__ __forceinline__ float q_lo(uint32_t w) { return __uint_as_float(0x4B000000u | (w & 0xffffu)) - 8388608.0f; }
+__device__ __forceinline__ float q_hi(uint32_t w) { return __uint_as_float(0x4B000000u | (w >> 16)) - 8388608.0f; }
+#endif
+
+// The ray in grid coordinates: per-axis scaling of origin and direction leaves t unchanged.
+struct GridRay {
+    float ox, oy, oz;     // (o - grid_lo) * grid_inv
+    float ix, iy, iz;     // 1 / (d * grid_inv); IEEE: a zero component gives +-inf, NaN drops out of fmin/fmax
+};
+__device__ __forceinline__ GridRay make_grid_ray(const SceneView& sc, V3 o, V3 d) {
+    GridRay g;
+    g.ox = (o.x - sc.grid_lo[0]) * sc.grid_inv[0];
+    g.oy = (o.y - sc.grid_lo[1]) * sc.grid_inv[1];
+    g.oz = (o.z - sc.grid_lo[2]) * sc.grid_inv[2];
+    g.ix = 1.0f / (d.x * sc.grid_inv[0]);
+    g.iy = 1.0f / (d.y * sc.grid_inv[1]);
+    g.iz = 1.0f / (d.z * sc.grid_inv[2]);
+    return g;
+}
+// Two slab tests against the quantised child boxes of one node.  Slabs as (plane - origin) * inv:
+// the subtraction is exact or nearly so, which keeps the test meaningful for rays almost parallel
+// to a slab (an fma of two huge products would cancel catastrophically there; an fma variant with
+// an explicit error bound was measured and lost: 3-register FFMA issues at half rate).  The far
+// side is widened by ~8 ulp so rounding can never cull a true hit.
+__device__ __forceinline__ void slab2(const uint32_t (&w)[8], const GridRay& g, float bestT, float& lNear,
+                                      float& rNear, bool& hitL, bool& hitR) {
+    const float kWiden = 1.000001f;
+    const float lx0 = (q_lo(w[0]) - g.ox) * g.ix, lx1 = (q_hi(w[0]) - g.ox) * g.ix;
+    const float ly0 = (q_lo(w[1]) - g.oy) * g.iy, ly1 = (q_hi(w[1]) - g.oy) * g.iy;
+    const float lz0 = (q_lo(w[2]) - g.oz) * g.iz, lz1 = (q_hi(w[2]) - g.oz) * g.iz;
+    const float rx0 = (q_lo(w[3]) - g.ox) * g.ix, rx1 = (q_hi(w[3]) - g.ox) * g.ix;
+    const float ry0 = (q_lo(w[4]) - g.oy) * g.iy, ry1 = (q_hi(w[4]) - g.oy) * g.iy;
+    const float rz0 = (q_lo(w[5]) - g.oz) * g.iz, rz1 = (q_hi(w[5]) - g.oz) * g.iz;
+    lNear = fmaxf(fmaxf(fminf(lx0, lx1), fminf(ly0, ly1)), fmaxf(fminf(lz0, lz1), 0.0f));
+    rNear = fmaxf(fmaxf(fminf(rx0, rx1), fminf(ry0, ry1)), fmaxf(fminf(rz0, rz1), 0.0f));
+    const float lFar = fminf(fminf(fmaxf(lx0, lx1), fmaxf(ly0, ly1)), fminf(fmaxf(lz0, lz1), bestT)) * kWiden;
+    const float rFar = fminf(fminf(fmaxf(rx0, rx1), fmaxf(ry0, ry1)), fminf(fmaxf(rz0, rz1), bestT)) * kWiden;
+    hitL = lNear <= lFar;
+    hitR = rNear <= rFar;
+}
+// first 48 bytes of a triangle record: a, e0, e1, N
+struct TriGeom {
+    V3 a, e0, e1, N;
+};
+__device__ __forceinline__ TriGeom load_tri(const SceneView& sc, int32_t s) {
+    float g[8];
+    asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(g[0]), "=f"(g[1]), "=f"(g[2]), "=f"(g[3]), "=f"(g[4]), "=f"(g[5]), "=f"(g[6]), "=f"(g[7])
+                 : "l"(sc.tri_geom + 4 * s));
+    const float4 h = __ldg(sc.tri_geom + 4 * s + 2);
+    TriGeom t;
+    t.a = v3(g[0], g[1], g[2]);
+    t.e0 = v3(g[3], g[4], g[5]);
+    t.e1 = v3(g[6], g[7], h.x);
+    t.N = v3(h.y, h.z, h.w);
+    return t;
+}
 __device__ __forceinline__ void ldg256(const void* p, float (&v)[8]) {
     asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                  : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7])
@@ -90,9 +165,8 @@ __device__ __forceinline__ HitRec closest_hit(const SceneView& sc, V3 o, V3 d, u
     int32_t bestOrig = 0x7fffffff;
     if (sc.num_tris <= 0) return best;
 
-    // IEEE division: a zero component gives +-inf; NaNs (inf*0) drop out of fminf/fmaxf
-    const float idx = 1.0f / d.x, idy = 1.0f / d.y, idz = 1.0f / d.z;
-    const float kWiden = 1.000001f;  // ~8 ulp: rounding in the slab test can never cull a true hit
+    const GridRay g = make_grid_ray(sc, o, d);
+    const float kWiden = 1.000001f;
 
     int32_t stack[kStackSize];
     float tstack[kStackSize];
@@ -101,26 +175,13 @@ __device__ __forceinline__ HitRec closest_hit(const SceneView& sc, V3 o, V3 d, u
 
     for (;;) {
         if (cur >= 0) {
-            float nl[8], nr[8];
-            ldg256(sc.nodes + 4 * cur, nl);
-            ldg256(sc.nodes + 4 * cur + 2, nr);
+            uint32_t w[8];
+            ldg256u(sc.nodes + 2 * cur, w);
             if (COUNT) nodeVisits++;
-            // slabs as (plane - origin) * inv: the subtraction is exact or nearly so, which keeps
-            // the test meaningful for rays almost parallel to a slab (an fma of two huge products
-            // would cancel catastrophically there)
-            const float lx0 = (nl[0] - o.x) * idx, lx1 = (nl[1] - o.x) * idx;
-            const float ly0 = (nl[2] - o.y) * idy, ly1 = (nl[3] - o.y) * idy;
-            const float lz0 = (nl[4] - o.z) * idz, lz1 = (nl[5] - o.z) * idz;
-            const float rx0 = (nr[0] - o.x) * idx, rx1 = (nr[1] - o.x) * idx;
-            const float ry0 = (nr[2] - o.y) * idy, ry1 = (nr[3] - o.y) * idy;
-            const float rz0 = (nr[4] - o.z) * idz, rz1 = (nr[5] - o.z) * idz;
-            const float lNear = fmaxf(fmaxf(fminf(lx0, lx1), fminf(ly0, ly1)), fmaxf(fminf(lz0, lz1), 0.0f));
-            const float rNear = fmaxf(fmaxf(fminf(rx0, rx1), fminf(ry0, ry1)), fmaxf(fminf(rz0, rz1), 0.0f));
-            const float lFar = fminf(fminf(fmaxf(lx0, lx1), fmaxf(ly0, ly1)), fminf(fmaxf(lz0, lz1), best.t)) * kWiden;
-            const float rFar = fminf(fminf(fmaxf(rx0, rx1), fmaxf(ry0, ry1)), fminf(fmaxf(rz0, rz1), best.t)) * kWiden;
-            const bool hitL = lNear <= lFar;
-            const bool hitR = rNear <= rFar;
-            const int32_t cl = __float_as_int(nl[6]), cr = __float_as_int(nl[7]);
+            float lNear, rNear;
+            bool hitL, hitR;
+            slab2(w, g, best.t, lNear, rNear, hitL, hitR);
+            const int32_t cl = (int32_t)w[6], cr = (int32_t)w[7];
             if (hitL && hitR) {
                 const bool leftFirst = lNear <= rNear;
                 stack[sp] = leftFirst ? cr : cl;
@@ -140,15 +201,12 @@ __device__ __forceinline__ HitRec closest_hit(const SceneView& sc, V3 o, V3 d, u
             const int32_t first = packed & kLeafFirstMask;
             const int32_t count = (packed >> kLeafCountShift) + 1;
             for (int32_t s = first; s < first + count; s++) {
-                float g[8], h[8];
-                ldg256(sc.tri_geom + 4 * s, g);
-                ldg256(sc.tri_geom + 4 * s + 2, h);
+                const TriGeom tg = load_tri(sc, s);
                 if (COUNT) triTests++;
                 float dst, u, v;
-                if (ray_triangle(o, d, v3(g[0], g[1], g[2]), v3(g[3], g[4], g[5]), v3(g[6], g[7], h[0]),
-                                 v3(h[1], h[2], h[3]), dst, u, v)) {
+                if (ray_triangle(o, d, tg.a, tg.e0, tg.e1, tg.N, dst, u, v)) {
                     if (dst <= best.t && dst < kMissT) {
-                        const int32_t orig = __float_as_int(h[4]);
+                        const int32_t orig = __ldg(&sc.tri_orig[s]);
                         if (dst < best.t || orig < bestOrig) {
                             best.t = dst;
                             best.u = u;

@@ -247,8 +247,8 @@ struct ExtendTune {
 // state (near child / push far child / pop).  v2's if/else ladder here ran at 3-8 active lanes
 // (profiles/r1_v2_extend_ncu_full.md); selects and one predicated store keep the warp converged.
 struct RayRegs {
-    V3 o, d;
-    float idx, idy, idz;
+    V3 o, d;      // world space: the exact triangle test
+    GridRay g;    // grid space: the slab tests
     float bestT;
 };
 // Traversal stack: the first kShStack entries of every lane live in shared memory laid out
@@ -270,23 +270,12 @@ struct Stack {
     }
 };
 __device__ __forceinline__ void node_step(const SceneView& sc, const RayRegs& r, int32_t& node, int& sp, Stack& st) {
-    const float kWiden = 1.000001f;
-    float nl[8], nr[8];
-    ldg256(sc.nodes + 4 * node, nl);
-    ldg256(sc.nodes + 4 * node + 2, nr);
-    const float lx0 = (nl[0] - r.o.x) * r.idx, lx1 = (nl[1] - r.o.x) * r.idx;
-    const float ly0 = (nl[2] - r.o.y) * r.idy, ly1 = (nl[3] - r.o.y) * r.idy;
-    const float lz0 = (nl[4] - r.o.z) * r.idz, lz1 = (nl[5] - r.o.z) * r.idz;
-    const float rx0 = (nr[0] - r.o.x) * r.idx, rx1 = (nr[1] - r.o.x) * r.idx;
-    const float ry0 = (nr[2] - r.o.y) * r.idy, ry1 = (nr[3] - r.o.y) * r.idy;
-    const float rz0 = (nr[4] - r.o.z) * r.idz, rz1 = (nr[5] - r.o.z) * r.idz;
-    const float lNear = fmaxf(fmaxf(fminf(lx0, lx1), fminf(ly0, ly1)), fmaxf(fminf(lz0, lz1), 0.0f));
-    const float rNear = fmaxf(fmaxf(fminf(rx0, rx1), fminf(ry0, ry1)), fmaxf(fminf(rz0, rz1), 0.0f));
-    const float lFar = fminf(fminf(fmaxf(lx0, lx1), fmaxf(ly0, ly1)), fminf(fmaxf(lz0, lz1), r.bestT)) * kWiden;
-    const float rFar = fminf(fminf(fmaxf(rx0, rx1), fmaxf(ry0, ry1)), fminf(fmaxf(rz0, rz1), r.bestT)) * kWiden;
-    const bool hitL = lNear <= lFar;
-    const bool hitR = rNear <= rFar;
-    const int32_t cl = __float_as_int(nl[6]), cr = __float_as_int(nl[7]);
+    uint32_t w[8];
+    ldg256u(sc.nodes + 2 * node, w);
+    float lNear, rNear;
+    bool hitL, hitR;
+    slab2(w, r.g, r.bestT, lNear, rNear, hitL, hitR);
+    const int32_t cl = (int32_t)w[6], cr = (int32_t)w[7];
     const bool both = hitL && hitR;
     const bool goLeft = hitL && (!hitR || lNear <= rNear);
     const int32_t nearC = goLeft ? cl : cr;
@@ -314,7 +303,8 @@ __global__ void __launch_bounds__(kExtBlock) k_extend(const __grid_constant__ Sc
     bool exhausted = (n == 0u) || sc.num_tris <= 0;
     uint32_t ray = 0;
     RayRegs r;
-    r.o = v3(0, 0, 0); r.d = v3(0, 0, 1); r.idx = r.idy = r.idz = 0.0f; r.bestT = kMissT;
+    r.o = v3(0, 0, 0); r.d = v3(0, 0, 1); r.bestT = kMissT;
+    r.g.ox = r.g.oy = r.g.oz = r.g.ix = r.g.iy = r.g.iz = 0.0f;
     float bestU = 0, bestV = 0;
     int32_t bestSlot = -1, bestOrig = 0x7fffffff;
     int32_t node = kIdle;
@@ -356,10 +346,7 @@ __global__ void __launch_bounds__(kExtBlock) k_extend(const __grid_constant__ Sc
                     ray = i;
                     r.o = v3(a.x, a.y, a.z);
                     r.d = v3(a.w, b.x, b.y);
-                    // IEEE division: a zero component gives +-inf; NaNs (inf*0) drop out of fminf/fmaxf
-                    r.idx = 1.0f / r.d.x;
-                    r.idy = 1.0f / r.d.y;
-                    r.idz = 1.0f / r.d.z;
+                    r.g = make_grid_ray(sc, r.o, r.d);
                     r.bestT = kMissT; bestU = 0.0f; bestV = 0.0f; bestSlot = -1; bestOrig = 0x7fffffff;
                     sp = 0;
                     node = sc.root_is_leaf ? pack_leaf(0, sc.num_tris) : 0;
@@ -381,15 +368,12 @@ __global__ void __launch_bounds__(kExtBlock) k_extend(const __grid_constant__ Sc
                 const int32_t first = packed & kLeafFirstMask;
                 const int32_t cnt = (packed >> kLeafCountShift) + 1;
                 for (int32_t s = first; s < first + cnt; s++) {
-                    float g[8], h[8];
-                    ldg256(sc.tri_geom + 4 * s, g);
-                    ldg256(sc.tri_geom + 4 * s + 2, h);
+                    const TriGeom tg = load_tri(sc, s);
                     if (COUNT) tests++;
                     float dst, u, v;
-                    if (ray_triangle(r.o, r.d, v3(g[0], g[1], g[2]), v3(g[3], g[4], g[5]), v3(g[6], g[7], h[0]),
-                                     v3(h[1], h[2], h[3]), dst, u, v)) {
+                    if (ray_triangle(r.o, r.d, tg.a, tg.e0, tg.e1, tg.N, dst, u, v)) {
                         if (dst <= r.bestT && dst < kMissT) {
-                            const int32_t orig = __float_as_int(h[4]);
+                            const int32_t orig = __ldg(&sc.tri_orig[s]);
                             if (dst < r.bestT || orig < bestOrig) {
                                 r.bestT = dst; bestU = u; bestV = v; bestSlot = s; bestOrig = orig;
                             }
