@@ -189,10 +189,10 @@ def run_gpu(args, rt):
 
     W, H = WORKLOAD["width"], WORKLOAD["height"]
     scene, cam, u = build_workload(rt, W, H)
-    frames = WORKLOAD["frames"] * world
+    frames = (args.frames if args.frames > 0 else WORKLOAD["frames"]) * world
     tris, mats, texs = scene.triangles, scene.materials, scene.textures
 
-    split = rt.SPLIT_FRAMES if world > 1 else rt.SPLIT_NONE
+    split = rt.SPLIT_NONE if world == 1 else (rt.SPLIT_TILES if args.split == "tiles" else rt.SPLIT_FRAMES)
     be = rt.Backend(device=local_rank, rng_mode=rt.RNG_PHILOX, split_mode=split, rank=rank, world_size=world,
                     kernel_timing=True)
     stream = torch.cuda.current_stream()
@@ -332,7 +332,8 @@ def run_gpu(args, rt):
         line = {
             "metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(world),
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": dict(workload_config(world), frames_total=frames,
+                                                  split=("none" if world == 1 else args.split)),
             "seconds_per_screenshot": ms_per_step * 1e-3,
             "segments_per_step": segments / args.steps,
             "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
@@ -357,6 +358,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--frames", type=int, default=0, help="frames per GPU (default 4 = 256 spp)")
+    ap.add_argument("--split", default="frames", choices=["frames", "tiles"],
+                    help="N > 1: frame-slice split + ncclReduce (default) or image-tile split + gather")
     args = ap.parse_args()
     rt = importlib.import_module("raytracing2-fork_b200")
     if args.impl == "reference":

@@ -101,7 +101,7 @@ struct rt_ctx {
     rt_config cfg{};
     int sm_count = 148;
     int extend_blocks_per_sm = 4;
-    int leaf_vote = 12, refill = 8;
+    int leaf_vote = 8, refill = 8, node_steps = 3;
     cudaStream_t own_stream = nullptr;
     cudaStream_t stream = nullptr;
     std::string err;
@@ -181,6 +181,7 @@ Launcher make_launcher(rt_ctx* ctx) {
     L.extend_grid = ctx->sm_count * ctx->extend_blocks_per_sm;
     L.leaf_vote = ctx->leaf_vote;
     L.refill = ctx->refill;
+    L.node_steps = ctx->node_steps;
     L.kernel_launches = &ctx->kernel_launches;
     L.extend_launches = &ctx->extend_launches;
     L.ev_pool = ctx->events.data();
@@ -459,6 +460,7 @@ int rt_create(rt_ctx** out, const rt_config* cfg) {
     // tuning knobs of the persistent traversal kernel (defaults chosen from ncu runs)
     if (const char* e1 = getenv("RT_EXT_LEAF_VOTE")) ctx->leaf_vote = std::max(1, std::min(32, atoi(e1)));
     if (const char* e2 = getenv("RT_EXT_REFILL")) ctx->refill = std::max(1, std::min(32, atoi(e2)));
+    if (const char* e4 = getenv("RT_EXT_NODE_STEPS")) ctx->node_steps = std::max(1, std::min(16, atoi(e4)));
     if (const char* e3 = getenv("RT_EXT_BLOCKS_PER_SM")) ctx->extend_blocks_per_sm = std::max(1, std::min(32, atoi(e3)));
     if (ctx->d_stats.reserve(4 * sizeof(unsigned long long)) != cudaSuccess ||
         cudaMemsetAsync(ctx->d_stats.p, 0, 4 * sizeof(unsigned long long), ctx->stream) != cudaSuccess) {

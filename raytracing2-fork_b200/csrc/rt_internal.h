@@ -71,6 +71,7 @@ struct Launcher {
     int extend_grid;   // persistent k_extend grid: SMs x resident blocks per SM
     int leaf_vote;     // k_extend: leaf step when this many lanes wait at a leaf
     int refill;        // k_extend: refill when this many lanes are idle
+    int node_steps;    // k_extend: node steps per vote
     uint64_t* kernel_launches;
     uint64_t* extend_launches;
     // optional per-class device timing

@@ -241,6 +241,7 @@ constexpr int32_t kIdle = (int32_t)0x80000001;      // lane state: no ray
 struct ExtendTune {
     int leafVote;  // leaf step when >= this many lanes wait at a leaf
     int refill;    // refill when >= this many lanes are idle
+    int nodeSteps; // node steps per vote
 };
 
 // One node step for a lane at an inner node: two slab tests, then a branch-free choice of the next
@@ -383,13 +384,13 @@ __global__ void __launch_bounds__(kExtBlock) k_extend(const __grid_constant__ Sc
                 node = kPop;
             }
         } else {
-            if (node >= 0) {
-                if (COUNT) visits++;
-                node_step(sc, r, node, sp, st);
-            }
-            if (node >= 0) {  // a second step before the next vote halves the voting overhead per step
-                if (COUNT) visits++;
-                node_step(sc, r, node, sp, st);
+            // several node steps per vote amortise the voting overhead (lanes that reach a leaf wait)
+#pragma unroll 1
+            for (int k = 0; k < tune.nodeSteps; k++) {
+                if (node >= 0) {
+                    if (COUNT) visits++;
+                    node_step(sc, r, node, sp, st);
+                }
             }
         }
     }
@@ -803,7 +804,7 @@ cudaError_t wf_render_batch(const Launcher& L, const SceneView& sc, const WaveBu
                                                                                 : (long long)L.sm_count * 8);
     const int extGrid = L.extend_grid;
     uint32_t* cursors = wb.counts + ncounts;
-    ExtendTune tune{L.leaf_vote, L.refill};
+    ExtendTune tune{L.leaf_vote, L.refill, L.node_steps};
     PathArrays a = wb.cur, b = wb.next;
     for (int bounce = 0; bounce < maxB; bounce++) {
         {
