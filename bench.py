@@ -60,7 +60,7 @@ class ClockSampler:
              "clocks_event_reasons.sw_power_cap")
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", os.environ.get("RT_BENCH_CLOCK_MS", "100")],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
@@ -195,7 +195,12 @@ def run_gpu(args, rt):
     split = rt.SPLIT_NONE if world == 1 else (rt.SPLIT_TILES if args.split == "tiles" else rt.SPLIT_FRAMES)
     be = rt.Backend(device=local_rank, rng_mode=rt.RNG_PHILOX, split_mode=split, rank=rank, world_size=world,
                     kernel_timing=True)
-    stream = torch.cuda.current_stream()
+    # The library launches on the stream it is given; torch's default stream is the legacy stream 0,
+    # which rt_set_stream treats as "use the ctx's own stream", and events recorded on stream 0 would
+    # not wait for that non-blocking stream.  So: one explicit side stream for library and events.
+    stream = torch.cuda.Stream(device=local_rank)
+    torch.cuda.set_stream(stream)
+    assert stream.cuda_stream != 0
     be.set_stream(stream.cuda_stream)
     if world > 1:
         obj = [be.comm_unique_id() if rank == 0 else None]
@@ -230,16 +235,20 @@ def run_gpu(args, rt):
     barrier()
     be.reset_counters()
     sampler = ClockSampler(local_rank)
-    if rank == 0:
+    if rank == 0 and not os.environ.get("RT_BENCH_NO_CLOCKS"):
         sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    step_ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
     ev0.record(stream)
-    for _ in range(args.steps):
+    step_ev[0].record(stream)
+    for i in range(args.steps):
         be.screenshot_device(u, frames)
+        step_ev[i + 1].record(stream)
     ev1.record(stream)
     barrier()
     ms_total = ev0.elapsed_time(ev1)
+    step_ms = [step_ev[i].elapsed_time(step_ev[i + 1]) for i in range(args.steps)]
     clocks = sampler.stop() if rank == 0 else None
     c = be.counters()
     t = torch.tensor([ms_total, float(c["segments"]), float(c["kernel_launches"])], dtype=torch.float64, device="cuda")
@@ -334,7 +343,7 @@ def run_gpu(args, rt):
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": dict(workload_config(world), frames_total=frames,
                                                   split=("none" if world == 1 else args.split)),
-            "seconds_per_screenshot": ms_per_step * 1e-3,
+            "seconds_per_screenshot": ms_per_step * 1e-3, "step_ms": [round(x, 2) for x in step_ms],
             "segments_per_step": segments / args.steps,
             "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "seconds_per_step": wall / n_e2e, "steps": n_e2e,

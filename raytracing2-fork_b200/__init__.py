@@ -152,7 +152,8 @@ def backend_lib() -> C.CDLL:
     """librt_b200.so (CUDA, sm_100a).  Raises if it has not been built: no fallback exists."""
     global _backend_lib
     if _backend_lib is None:
-        path = os.path.join(_HERE, "librt_b200.so")
+        # RT_B200_LIB: another build of the SAME C-ABI (used only to A/B older kernel versions)
+        path = os.environ.get("RT_B200_LIB") or os.path.join(_HERE, "librt_b200.so")
         if not os.path.exists(path):
             raise BackendError(f"{path} missing — the CUDA backend is required (no CPU fallback); "
                                f"run `make -C {_HERE}` or __graft_entry__.build()")

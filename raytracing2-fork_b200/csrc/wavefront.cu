@@ -407,9 +407,74 @@ __global__ void __launch_bounds__(kExtBlock) k_extend(const __grid_constant__ Sc
     }
 }
 
+// The random numbers one bounce consumes (S:503-552): the rejection-sampled unit vector (3 draws per
+// try) when the material scatters diffusely, then `nExtra` more draws (specular choice, Russian roulette).
+struct BounceRandoms {
+    V3 randDir;
+    float d0, d1;
+};
+// RT_RNG_REF_PCG: the reference's sequential stream, drawn exactly in shader order.
+__device__ __forceinline__ BounceRandoms bounce_randoms(Rng<0>& rng, bool needDir, int nExtra) {
+    BounceRandoms r;
+    r.randDir = v3(0.0f, 0.0f, 0.0f);
+    r.d0 = r.d1 = 0.0f;
+    if (needDir) r.randDir = random_direction(rng);
+    if (nExtra >= 1) r.d0 = rng.next();
+    if (nExtra >= 2) r.d1 = rng.next();
+    return r;
+}
+// RT_RNG_PHILOX: draw j of a bounce is a pure function of (pixel, frame, sample, bounce, j), so the first
+// twelve draws (three Philox blocks = three rejection tries + the two extra draws after any of them) are
+// generated up front by the whole warp in lock step and the tries are evaluated with selects.  ncu on the
+// sequential version showed 9.5 of 32 lanes active per instruction in k_shade, most of it the divergent
+// rejection loop and the on-demand block generation.  Only the 11 % of lanes whose first three tries all
+// fail continue in the sequential loop (from draw 9).  Values and draw indices are identical to the
+// sequential definition, so no bit of the image changes.
+__device__ __forceinline__ BounceRandoms bounce_randoms(Rng<1>& rng, bool needDir, int nExtra) {
+    uint32_t w[12];
+    philox4x32_10(0u, rng.bounce, rng.sample, 0x52543230u, rng.pixel, rng.frame, &w[0]);
+    philox4x32_10(1u, rng.bounce, rng.sample, 0x52543230u, rng.pixel, rng.frame, &w[4]);
+    philox4x32_10(2u, rng.bounce, rng.sample, 0x52543230u, rng.pixel, rng.frame, &w[8]);
+    float f[12];
+#pragma unroll
+    for (int i = 0; i < 12; i++) f[i] = u32_to_unit(w[i]);
+    BounceRandoms r;
+    r.randDir = v3(0.0f, 0.0f, 0.0f);
+    r.d0 = f[0];
+    r.d1 = f[1];
+    if (needDir) {
+        const V3 c1 = v3(f[0] * 2.0f - 1.0f, f[1] * 2.0f - 1.0f, f[2] * 2.0f - 1.0f);
+        const V3 c2 = v3(f[3] * 2.0f - 1.0f, f[4] * 2.0f - 1.0f, f[5] * 2.0f - 1.0f);
+        const V3 c3 = v3(f[6] * 2.0f - 1.0f, f[7] * 2.0f - 1.0f, f[8] * 2.0f - 1.0f);
+        const bool a1 = length(c1) < 1.0f, a2 = length(c2) < 1.0f, a3 = length(c3) < 1.0f;
+        if (a1 || a2 || a3) {
+            const V3 c = a1 ? c1 : (a2 ? c2 : c3);
+            r.randDir = normalize(c);
+            r.d0 = a1 ? f[3] : (a2 ? f[6] : f[9]);
+            r.d1 = a1 ? f[4] : (a2 ? f[7] : f[10]);
+        } else {
+            // tries 4..100 of S:176-183, sequentially, starting at draw 9 (block 2 is already in hand)
+            rng.j = 9u;
+            rng.cache[0] = w[8]; rng.cache[1] = w[9]; rng.cache[2] = w[10]; rng.cache[3] = w[11];
+            for (int i = 3; i < 100; i++) {
+                const float x = rng.next() * 2.0f - 1.0f;
+                const float y = rng.next() * 2.0f - 1.0f;
+                const float z = rng.next() * 2.0f - 1.0f;
+                if (length(v3(x, y, z)) < 1.0f) {
+                    r.randDir = normalize(v3(x, y, z));
+                    break;
+                }
+            }
+            if (nExtra >= 1) r.d0 = rng.next();
+            if (nExtra >= 2) r.d1 = rng.next();
+        }
+    }
+    return r;
+}
+
 // One bounce of S:481-560 for every live path.  `bounce` is the 0-based index of this segment.
 template <int MODE>
-__global__ void __launch_bounds__(kBlock) k_shade(const __grid_constant__ SceneView sc,
+__global__ void __launch_bounds__(kBlock, 4) k_shade(const __grid_constant__ SceneView sc,
                                                   const __grid_constant__ FrameParams fp, PathArrays cur,
                                                   PathArrays next, const float4* __restrict__ hit,
                                                   float4* __restrict__ contrib, uint32_t* __restrict__ pix_rng,
@@ -445,10 +510,18 @@ __global__ void __launch_bounds__(kBlock) k_shade(const __grid_constant__ SceneV
             const int32_t hslot = __float_as_int(h.w);
             bool terminated = false;
             V3 radiance = v3(0.0f, 0.0f, 0.0f);
+            Material m;
+            m.type = -1;
+            if (hslot >= 0) {
+                const float4 s1 = __ldg(&sc.tri_shade[2 * hslot + 1]);
+                m = load_material(sc, __float_as_int(s1.z));
+            }
+            const bool needDir = hslot >= 0 && (m.type == RT_MAT_DIFFUSE || m.type == RT_MAT_TEXTURE ||
+                                                m.type == RT_MAT_SPECULAR || m.type == RT_MAT_CHECKER);
+            const int nExtra = (hslot < 0) ? 0 : (m.type == RT_MAT_SPECULAR ? 2 : ((needDir || m.type == RT_MAT_GLASS) ? 1 : 0));
+            const BounceRandoms rnd = bounce_randoms(rng, needDir, nExtra);
             if (hslot >= 0) {
                 const float dst = h.x, bu = h.y, bv = h.z;
-                const float4 s1 = __ldg(&sc.tri_shade[2 * hslot + 1]);
-                const Material m = load_material(sc, __float_as_int(s1.z));
                 const V3 hitPoint = o + d * dst;        // S:330
                 const V3 normal = tri_normal(sc, hslot);
                 if (m.type != RT_MAT_GLASS)
@@ -457,10 +530,11 @@ __global__ void __launch_bounds__(kBlock) k_shade(const __grid_constant__ SceneV
                     o = hitPoint + (d * dst) * -1e-3f;  // S:492
                 V3 attenuation = v3(0.0f, 0.0f, 0.0f);
                 const V3 prevDirection = d;
+                float rrDraw = rnd.d0;
                 switch (m.type) {
                     case RT_MAT_DIFFUSE:
                     case RT_MAT_TEXTURE: {
-                        d = normalize(normal + random_direction(rng));
+                        d = normalize(normal + rnd.randDir);
                         if (m.type == RT_MAT_DIFFUSE)
                             attenuation = m.color;
                         else
@@ -469,11 +543,12 @@ __global__ void __launch_bounds__(kBlock) k_shade(const __grid_constant__ SceneV
                         break;
                     }
                     case RT_MAT_SPECULAR: {
-                        const V3 diffuseDirection = normalize(normal + random_direction(rng));
+                        const V3 diffuseDirection = normalize(normal + rnd.randDir);
                         const V3 specularDirection = reflect(d, normal);
-                        const bool isSpecularBounce = m.specularProbability > rng.next();
+                        const bool isSpecularBounce = m.specularProbability > rnd.d0;
                         d = mix(diffuseDirection, specularDirection, isSpecularBounce ? m.smoothness : 0.0f);
                         attenuation = isSpecularBounce ? v3(1.0f, 1.0f, 1.0f) : m.color;
+                        rrDraw = rnd.d1;
                         break;
                     }
                     case RT_MAT_LIGHT: {
@@ -483,7 +558,7 @@ __global__ void __launch_bounds__(kBlock) k_shade(const __grid_constant__ SceneV
                         break;
                     }
                     case RT_MAT_CHECKER: {
-                        d = normalize(normal + random_direction(rng));
+                        d = normalize(normal + rnd.randDir);
                         attenuation = black_checker(o, m.checkerScale) ? v3(0.0f, 0.0f, 0.0f) : v3(1.0f, 1.0f, 1.0f);
                         break;
                     }
@@ -506,7 +581,7 @@ __global__ void __launch_bounds__(kBlock) k_shade(const __grid_constant__ SceneV
                     else
                         rayColor = rayColor * attenuation;
                     const float p = gmax(rayColor.x, gmax(rayColor.y, rayColor.z));  // S:549-552
-                    if (rng.next() > p) {
+                    if (rrDraw > p) {
                         terminated = true;
                     } else {
                         rayColor = rayColor * (1.0f / p);
