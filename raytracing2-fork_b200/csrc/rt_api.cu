@@ -102,6 +102,7 @@ struct rt_ctx {
     int sm_count = 148;
     int extend_blocks_per_sm = 4;
     int leaf_vote = 8, refill = 8, node_steps = 3;
+    int use_ploc = 1;
     cudaStream_t own_stream = nullptr;
     cudaStream_t stream = nullptr;
     std::string err;
@@ -460,6 +461,7 @@ int rt_create(rt_ctx** out, const rt_config* cfg) {
     // tuning knobs of the persistent traversal kernel (defaults chosen from ncu runs)
     if (const char* e1 = getenv("RT_EXT_LEAF_VOTE")) ctx->leaf_vote = std::max(1, std::min(32, atoi(e1)));
     if (const char* e2 = getenv("RT_EXT_REFILL")) ctx->refill = std::max(1, std::min(32, atoi(e2)));
+    if (const char* e5 = getenv("RT_BVH_BUILDER")) ctx->use_ploc = strcmp(e5, "lbvh") != 0;
     if (const char* e4 = getenv("RT_EXT_NODE_STEPS")) ctx->node_steps = std::max(1, std::min(16, atoi(e4)));
     if (const char* e3 = getenv("RT_EXT_BLOCKS_PER_SM")) ctx->extend_blocks_per_sm = std::max(1, std::min(32, atoi(e3)));
     if (ctx->d_stats.reserve(4 * sizeof(unsigned long long)) != cudaSuccess ||
@@ -569,8 +571,8 @@ int rt_scene_build(rt_ctx* ctx) {
     CK(ctx->d_children.reserve(2 * nn * sizeof(int32_t)));
     CK(ctx->d_parent.reserve((size_t)(2 * n) * sizeof(int32_t)));
     CK(ctx->d_boxes.reserve((size_t)(2 * n) * 2 * sizeof(float4)));
-    CK(ctx->d_flags.reserve(nn * sizeof(uint32_t)));
-    CK(ctx->d_node_depth.reserve(nn * sizeof(uint32_t)));
+    CK(ctx->d_flags.reserve(((size_t)n + 1) * sizeof(uint32_t)));
+    CK(ctx->d_node_depth.reserve((size_t)(2 * n) * sizeof(uint32_t)));
     CK(ctx->d_depth.reserve(sizeof(uint32_t)));
     CK(ctx->d_nodes.reserve(nn * 2 * sizeof(uint4)));
     CK(ctx->d_grid.reserve(6 * sizeof(float)));
@@ -580,6 +582,7 @@ int rt_scene_build(rt_ctx* ctx) {
     BuildArgs a;
     a.tris = ctx->d_tris.as<rt_triangle>();
     a.n = n;
+    a.use_ploc = ctx->use_ploc;
     a.centroid = ctx->d_centroid.as<float4>();
     a.bounds = ctx->d_bounds.as<uint32_t>();
     for (int i = 0; i < 2; i++) {

@@ -12,6 +12,7 @@ namespace rt {
 struct BuildArgs {
     const rt_triangle* tris;  // device copy of the caller's array (original order)
     int n;
+    int use_ploc;             // 1 = PLOC hierarchy (default), 0 = Karras LBVH
     float4* centroid;         // n
     uint32_t* bounds;         // 12 order-preserving uints
     uint64_t* keys[2];        // n each
@@ -20,8 +21,8 @@ struct BuildArgs {
     int32_t* children;        // 2*(n-1)
     int32_t* parent;          // 2n-1
     float4* boxes;            // 2*(2n-1)
-    uint32_t* flags;          // n-1
-    uint32_t* nodeDepth;      // n-1 (height of the subtree under each inner node)
+    uint32_t* flags;          // n+1
+    uint32_t* nodeDepth;      // 2n (height of the subtree under each inner node / entity)
     uint32_t* maxDepth;       // 1
     float* grid;              // 6: quantisation grid (output)
     uint4* nodes;             // 2*(n-1)   (output)
