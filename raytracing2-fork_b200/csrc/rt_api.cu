@@ -617,6 +617,16 @@ int rt_scene_build(rt_ctx* ctx) {
     cudaEventDestroy(e1);
     ctx->build_ms = ms;
     ctx->bvh_depth = depth;
+    if ((int)depth + 1 >= kStackSize && a.use_ploc) {
+        // agglomerative clustering can chain (one big cluster absorbing neighbours round after round);
+        // the Karras tree over the same Morton order is at most key-bits deep
+        a.use_ploc = 0;
+        CK(build_lbvh(a, ctx->stream, &ctx->kernel_launches));
+        CK(cudaMemcpyAsync(&depth, ctx->d_depth.p, sizeof depth, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaMemcpyAsync(ctx->grid, ctx->d_grid.p, sizeof ctx->grid, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        ctx->bvh_depth = depth;
+    }
     if ((int)depth + 1 >= kStackSize)
         return fail(ctx, RT_ERR_INVALID, "rt_scene_build: BVH deeper than the traversal stack (" + std::to_string(depth) + ")");
     ctx->built = true;

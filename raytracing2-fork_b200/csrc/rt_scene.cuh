@@ -43,7 +43,7 @@ struct HitRec {
     int32_t slot;  // sorted slot, -1 = miss
 };
 
-constexpr int kStackSize = 64;
+constexpr int kStackSize = 128;
 
 // 256-bit read-only global load (sm_100a: LDG.E.ENL2.256.CONSTANT): one instruction, one L1TEX
 // wavefront per lane for 32 bytes, where four 128-bit loads of a 64-byte record would cost four.

@@ -419,14 +419,16 @@ int rth_add_displaced_sphere(rth_scene* s, int32_t n, const float center[3], flo
     const double PI_D = 3.14159265358979323846;
     std::vector<V3> v((size_t)(n + 1) * n);
     for (int i = 0; i <= n; i++) {
-        // rows stop half a step short of the poles: no degenerate triangles, 2n² in total
-        const double theta = PI_D * ((double)i + 0.5) / ((double)n + 1.0);
+        // the first and last rows collapse onto the poles, so the surface is closed; the n triangles
+        // per pole that degenerate to a segment have zero area and can never be hit (2n² in total)
+        const double theta = PI_D * (double)i / (double)n;
+        const double sinTheta = (i == 0 || i == n) ? 0.0 : std::sin(theta);
         for (int j = 0; j < n; j++) {
             const double phi = 2.0 * PI_D * (double)j / (double)n;
             const double r = (double)radius * (1.0 + (double)amp * std::sin(8.0 * theta) * std::sin(6.0 * phi));
-            v[(size_t)i * n + j] = V3{(float)((double)center[0] + r * std::sin(theta) * std::cos(phi)),
+            v[(size_t)i * n + j] = V3{(float)((double)center[0] + r * sinTheta * std::cos(phi)),
                                       (float)((double)center[1] + r * std::cos(theta)),
-                                      (float)((double)center[2] + r * std::sin(theta) * std::sin(phi))};
+                                      (float)((double)center[2] + r * sinTheta * std::sin(phi))};
         }
     }
     s->tris.reserve(s->tris.size() + (size_t)2 * n * n);

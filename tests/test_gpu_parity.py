@@ -167,7 +167,7 @@ def test_bvh_is_valid(sphere_box):
     rlo, rhi = visit(0)
     assert seen.all()
     assert (rlo <= tlo.min(0)).all() and (rhi >= thi.max(0)).all()
-    assert be.counters()["bvh_depth"] < 64
+    assert be.counters()["bvh_depth"] < 128
 
 
 @pytest.mark.parametrize("rng_mode", [rt.RNG_REF_PCG, rt.RNG_PHILOX])
@@ -356,3 +356,70 @@ def test_large_mesh_properties():
     assert_image_equal(be_small.read_frame(), a, "path budget independence")
     ref = orc.render_frame(u, rng_mode=rt.RNG_PHILOX)
     assert_image_equal(a, ref, "100k-triangle frame vs oracle")
+
+
+def test_both_hierarchy_builders_give_identical_hits(monkeypatch):
+    """PLOC (default) and the Karras LBVH are different trees over the same triangles; the closest-hit rule
+    makes the answer independent of the hierarchy, so ids, distances and whole frames must be identical."""
+    scene = rt.scene_textured_sphere(n_quads=48, container="mirror", tex_size=64)
+    o, d = random_rays(20000, 11, -3.8, 3.8)
+    cam = rt.camera_for_box(scene, 128, 72)
+    u = rt.screenshot_uniforms(scene, cam, spp=4, max_bounce=16, env_light=False)
+    results = []
+    for builder in ("ploc", "lbvh"):
+        monkeypatch.setenv("RT_BVH_BUILDER", builder)
+        be = backend(scene)
+        tri, dst, bu, bv = be.trace_rays(o, d)
+        be.render_frame(u)
+        results.append((tri, dst, bu, bv, be.read_frame(), be.counters()["bvh_depth"]))
+        be.close()
+    a, b = results
+    assert np.array_equal(a[0], b[0]) and np.array_equal(bits(a[1]), bits(b[1]))
+    assert np.array_equal(bits(a[2]), bits(b[2])) and np.array_equal(bits(a[3]), bits(b[3]))
+    assert_image_equal(a[4], b[4], "PLOC vs LBVH frame")
+    orc = oracle.OracleScene.from_scene(scene)
+    assert_image_equal(a[4], orc.render_frame(u, rng_mode=rt.RNG_PHILOX), "mirror box depth 16 vs oracle")
+
+
+def test_config4_scale_mesh_properties():
+    """BASELINE config 4's mesh at full size: 2*2236^2 = 9 999 392 triangles in the classic Cornell room.
+    Too large for the oracle; checked through size-independent properties: the build succeeds within the
+    traversal stack, every ray fired from inside the closed room hits something, rays aimed at the sphere
+    from outside its bounding radius hit the SPHERE (ids >= 14) at a distance consistent with its radius,
+    tracing is deterministic, and the tile-split partial sums of 2 emulated ranks add up exactly."""
+    scene = rt.scene_big_sphere(n_quads=2236)
+    assert scene.triangles.size == 14 + 2 * 2236 * 2236
+    be = backend(scene)
+    c = be.counters()
+    assert c["bvh_nodes"] == scene.triangles.size - 1 and c["bvh_depth"] < 128
+    o, d = random_rays(200000, 21, -4.9, 4.9)
+    tri, dst, _, _ = be.trace_rays(o, d)
+    inside = np.linalg.norm(o - np.array([0, -1, 0], np.float32), axis=1) < 2.8   # inside the sphere: back faces culled
+    assert (tri[~inside] >= 0).mean() > 0.999
+    # rays from the room towards the sphere centre
+    far = np.linalg.norm(o - np.array([0, -1, 0], np.float32), axis=1) > 3.3
+    oc = o[far]
+    dc = (np.array([0, -1, 0], np.float32) - oc)
+    dist_c = np.linalg.norm(dc, axis=1, keepdims=True)
+    dc = (dc / dist_c).astype(np.float32)
+    t2, d2, _, _ = be.trace_rays(oc, dc)
+    # The reference's Moller-Trumbore test is not watertight: a ray through a shared edge can be rejected by
+    # both neighbours (u, v or 1-u-v = -1e-7), and then continues through the culled back side to a wall.
+    # One such ray in 168 124 was checked by hand against the exact CPU test (no candidate triangle
+    # accepts it), so the property asserted is "all but a crack-sized fraction".
+    on_sphere = t2 >= 14
+    assert on_sphere.mean() > 0.9999
+    r_hit = dist_c[on_sphere, 0] - d2[on_sphere]
+    assert r_hit.min() > 3.0 * 0.94 and r_hit.max() < 3.0 * 1.06     # r = 3 (1 +- 0.05)
+    t3, d3, _, _ = be.trace_rays(oc, dc)
+    assert np.array_equal(t2, t3) and np.array_equal(bits(d2), bits(d3))
+    cam = rt.make_camera(96, 54, (0.0, 0.0, 15.5))
+    u = rt.screenshot_uniforms(scene, cam, spp=2, max_bounce=8, env_light=False)
+    total = be.screenshot_partial(u, 2)
+    be.close()
+    acc = np.zeros_like(total)
+    for rank in range(2):
+        b2 = backend(scene, split_mode=rt.SPLIT_TILES, rank=rank, world_size=2, band_rows=8)
+        acc += b2.screenshot_partial(u, 2)
+        b2.close()
+    assert np.array_equal(acc, total)
