@@ -265,6 +265,10 @@ class Scene:
         ch = 1 if px.ndim == 2 else px.shape[2]
         self._chk(self.L.rth_set_texture(self.h, slot, _ptr(px), w, h, ch))
 
+    def load_model_folder(self, folder: str):
+        """getTrianglesData_(folder, ...) of mesh.h:279 on a fresh scene (OBJ + MTL + textures/*.png)."""
+        self._chk(self.L.rth_load_model_folder(self.h, folder.encode()))
+
     def save(self, path):
         self._chk(self.L.rth_scene_save(self.h, path.encode()))
 

@@ -173,6 +173,7 @@ const int kWallsInward[12][3] = {{0, 3, 1}, {0, 2, 3}, {0, 5, 4}, {0, 1, 5}, {0,
 extern "C" {
 
 const char* rth_last_error(void) { return g_err.c_str(); }
+void rth_set_error(const char* msg) { g_err = msg ? msg : ""; }
 
 rth_scene* rth_scene_create(void) {
     rth_scene* s = new rth_scene;
@@ -199,6 +200,11 @@ const uint8_t* rth_scene_texture(const rth_scene* s, int32_t slot, int32_t* w, i
     return s->tex[slot].px.data();
 }
 
+int rth_scene_replace_materials(rth_scene* s, const rt_material* mats, int32_t count) {
+    if (!s || !mats || count <= 0) { g_err = "rth_scene_replace_materials: bad argument"; return RT_ERR_INVALID; }
+    s->mats.assign(mats, mats + count);
+    return RT_OK;
+}
 int32_t rth_add_material(rth_scene* s, const rt_material* m) {
     s->mats.push_back(*m);
     return (int32_t)s->mats.size() - 1;

@@ -28,6 +28,7 @@ typedef struct rth_scene rth_scene;
 rth_scene* rth_scene_create(void);   /* holds the `_default_` material (mesh.h:322-324) at index 0 */
 void rth_scene_destroy(rth_scene* s);
 const char* rth_last_error(void);
+void rth_set_error(const char* msg);  /* used by the translation units of this library */
 
 int64_t rth_scene_triangle_count(const rth_scene* s);
 const rt_triangle* rth_scene_triangles(const rth_scene* s);
@@ -35,6 +36,16 @@ int32_t rth_scene_material_count(const rth_scene* s);
 const rt_material* rth_scene_materials(const rth_scene* s);
 int32_t rth_scene_texture_count(const rth_scene* s);
 const uint8_t* rth_scene_texture(const rth_scene* s, int32_t slot, int32_t* w, int32_t* h, int32_t* ch);
+
+/* model folder ----------------------------------------------------------------------------------
+ * getTrianglesData_(folder, …) of mesh.h:279-613: first .obj of the folder, every .mtl, textures/
+ * (PNG decoded here; JPEG not yet).  Fills triangles, the material table in the reference's std::map
+ * order, and up to 5 textures (flipped vertically like stbi_set_flip_vertically_on_load(true)).
+ * The scene must be fresh.  Follow with rth_add_fixed_materials + a container, as main() does. */
+int rth_load_model_folder(rth_scene* s, const char* folder);
+/* PNG → 8-bit pixels with stbi_load(…, 0) channel conventions (top-down).  out == NULL: sizes only. */
+int rth_decode_png(const uint8_t* bytes, int64_t n, uint8_t* out, int64_t cap, int32_t* w, int32_t* h, int32_t* ch);
+int rth_scene_replace_materials(rth_scene* s, const rt_material* mats, int32_t count);
 
 /* materials ------------------------------------------------------------------------------------ */
 int32_t rth_add_material(rth_scene* s, const rt_material* m); /* returns its index */

@@ -9,7 +9,7 @@
 // pixel, Ctrl+S screenshot), each interactive frame is one rt_render_frame with the preview
 // uniforms (:1386-1400), and Ctrl+S runs rt_screenshot and writes Images/test.png (:261-264).
 //
-//   rt_shell [--model file.rtsc | --synthetic sphere:N] [--container none|classic|cornell|mirror|sidelit|sky]
+//   rt_shell [--folder RayTracing/Data/<model> | --model file.rtsc | --synthetic sphere:N] [--container none|classic|cornell|mirror|sidelit|sky]
 //            [--width W --height H] [--camera x,y,z] [--keys "W:0.5,A:0.25,z:1,X:0.5"]
 //            [--frames F --spp S --bounces B --env 0|1] [--rng pcg|philox] [--device D]
 //            [--out RayTracing/Images/test.png] [--preview preview.png]
@@ -40,14 +40,15 @@ struct KeyEvent {
 int main(int argc, char** argv) {
     rth_defaults d;
     rth_get_defaults(&d);
-    std::string model, synthetic, container = "none", keys, out = "test.png", preview;
+    std::string folder, model, synthetic, container = "none", keys, out = "test.png", preview;
     int W = d.scr_width, H = d.scr_height, device = 0;
     int frames = d.screenshot_frames, spp = d.screenshot_rays_per_pixel, bounces = d.screenshot_max_bounce_count;
     int env = d.screenshot_environmental_light, rng = RT_RNG_PHILOX;
     float cam[3] = {d.camera_pos[0], d.camera_pos[1], d.camera_pos[2]};
     for (int i = 1; i < argc; i++) {
         auto arg = [&](const char* n) { return strcmp(argv[i], n) == 0 && i + 1 < argc; };
-        if (arg("--model")) model = argv[++i];
+        if (arg("--folder")) folder = argv[++i];  // what the folder dialog returns in the reference (rayTracing.cpp:1249)
+        else if (arg("--model")) model = argv[++i];
         else if (arg("--synthetic")) synthetic = argv[++i];
         else if (arg("--container")) container = argv[++i];
         else if (arg("--width")) W = atoi(argv[++i]);
@@ -67,7 +68,10 @@ int main(int argc, char** argv) {
 
     // ---- scene assembly (main(), rayTracing.cpp:1258-1291)
     rth_scene* scene = rth_scene_create();
-    if (!model.empty()) {
+    if (!folder.empty()) {
+        printf("Loading model, please wait...\n");
+        if (rth_load_model_folder(scene, folder.c_str()) != RT_OK) die("cannot load model folder", rth_last_error());
+    } else if (!model.empty()) {
         if (rth_scene_load(scene, model.c_str()) != RT_OK) die("cannot load model", rth_last_error());
     } else if (!synthetic.empty()) {
         int n = 64;
