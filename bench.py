@@ -38,9 +38,29 @@ WORKLOAD = dict(width=1920, height=1080, spp_per_frame=64, frames=4, max_bounce=
 CPU_SAMPLE = dict(crop_w=480, crop_h=270, frames=1, spp=4)  # bounded CPU sample of the same workload
 
 
+# The other BASELINE configs (parity-test cases; `--workload` measures them for the record, the default
+# bench line is always config 2).
+OTHER_WORKLOADS = {
+    "config1": dict(width=512, height=512, frames=1, max_bounce=8),
+    "config3": dict(width=1920, height=1080, frames=8, max_bounce=16),
+    "config4": dict(width=3840, height=2160, frames=16, max_bounce=8),
+}
+
+
 def build_workload(rt, width, height):
-    scene = rt.scene_textured_sphere(n_quads=WORKLOAD["n_quads"], container="cornell", tex_size=WORKLOAD["tex_size"])
-    cam = rt.camera_for_box(scene, width, height)
+    name = os.environ.get("RT_BENCH_WORKLOAD", "config2")
+    if name == "config1":
+        scene = rt.scene_classic_cornell()
+        cam = rt.make_camera(width, height, (0.0, 0.0, 15.5))
+    elif name == "config3":
+        scene = rt.scene_textured_sphere(n_quads=WORKLOAD["n_quads"], container="mirror", tex_size=WORKLOAD["tex_size"])
+        cam = rt.camera_for_box(scene, width, height)
+    elif name == "config4":
+        scene = rt.scene_big_sphere(n_quads=2236)
+        cam = rt.make_camera(width, height, (0.0, 0.0, 15.5))
+    else:
+        scene = rt.scene_textured_sphere(n_quads=WORKLOAD["n_quads"], container="cornell", tex_size=WORKLOAD["tex_size"])
+        cam = rt.camera_for_box(scene, width, height)
     u = rt.screenshot_uniforms(scene, cam, spp=WORKLOAD["spp_per_frame"], max_bounce=WORKLOAD["max_bounce"],
                                env_light=False)
     return scene, cam, u
@@ -158,6 +178,9 @@ def run_reference(args, rt):
 
 
 def workload_config(n_gpus):
+    if os.environ.get("RT_BENCH_WORKLOAD", "config2") != "config2":
+        return {"workload": "BASELINE " + os.environ["RT_BENCH_WORKLOAD"] + f" ({WORKLOAD['width']}x{WORKLOAD['height']}, "
+                f"{WORKLOAD['frames']} frames x 64 spp per GPU, depth {WORKLOAD['max_bounce']})", "frames_total": WORKLOAD["frames"] * n_gpus}
     return {
         "workload": "BASELINE config 2: Cornell box (addCornellBox 0.17/0.3, light 15.0) + synthetic textured "
                     "displaced sphere 100 352 triangles + 16 container triangles, 1920x1080, 256 spp = 4 frames x 64 spp "
@@ -210,7 +233,9 @@ def run_gpu(args, rt):
 
     # parity gate without the oracle: first-hit ids of the workload scene against the committed golden
     gate = None
-    if rank == 0:
+    if rank == 0 and args.workload != "config2":
+        gate = "n/a (golden is for config 2)"
+    elif rank == 0:
         try:
             meta = json.load(open(os.path.join(REPO, "tests", "golden", "golden.json")))
             cam_s = rt.camera_for_box(scene, 240, 135)
@@ -368,9 +393,14 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--frames", type=int, default=0, help="frames per GPU (default 4 = 256 spp)")
+    ap.add_argument("--workload", default="config2", choices=["config1", "config2", "config3", "config4"],
+                    help="BASELINE config to measure (default and contract: config2)")
     ap.add_argument("--split", default="frames", choices=["frames", "tiles"],
                     help="N > 1: frame-slice split + ncclReduce (default) or image-tile split + gather")
     args = ap.parse_args()
+    if args.workload != "config2":
+        os.environ["RT_BENCH_WORKLOAD"] = args.workload
+        WORKLOAD.update(OTHER_WORKLOADS[args.workload])
     rt = importlib.import_module("raytracing2-fork_b200")
     if args.impl == "reference":
         run_reference(args, rt)
