@@ -420,7 +420,8 @@ __global__ void __launch_bounds__(256) k_ploc_merge(const int32_t* __restrict__ 
                                                     int m, int n, const uint32_t* __restrict__ keepPos,
                                                     const uint32_t* __restrict__ mergePos, int firstId,
                                                     float4* __restrict__ boxes, int32_t* __restrict__ children,
-                                                    uint32_t* __restrict__ height, int32_t* __restrict__ clusterOut) {
+                                                    uint32_t* __restrict__ height, int32_t* __restrict__ parentOf,
+                                                    uint32_t* __restrict__ innerCount, int32_t* __restrict__ clusterOut) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= m) return;
     const int j = nn[i];
@@ -437,9 +438,34 @@ __global__ void __launch_bounds__(256) k_ploc_merge(const int32_t* __restrict__ 
         children[2 * id] = a;
         children[2 * id + 1] = b;
         height[id] = max(height[ea], height[eb]) + 1u;
+        // bookkeeping for the depth-first relabelling: parent links and inner nodes per subtree
+        if (a >= 0) parentOf[a] = id;
+        if (b >= 0) parentOf[b] = id;
+        innerCount[id] = 1u + (a >= 0 ? innerCount[a] : 0u) + (b >= 0 ? innerCount[b] : 0u);
         c = id;
     }
     clusterOut[keepPos[i]] = c;
+}
+
+// Depth-first (pre-order) position of every inner node: walk up to the root adding 1 per level and
+// the size of the left sibling's subtree whenever the node is a right child.  A left child then sits
+// right behind its parent — in the same 128-byte line three times out of four — and every subtree is
+// contiguous in memory.
+__global__ void __launch_bounds__(256) k_dfs_order(int n, const int32_t* __restrict__ children,
+                                                   const int32_t* __restrict__ parentOf,
+                                                   const uint32_t* __restrict__ innerCount, int32_t* __restrict__ order) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n - 1) return;
+    uint32_t pos = 0;
+    int node = i;
+    while (node != 0) {
+        const int p = parentOf[node];
+        const int32_t left = children[2 * p];
+        pos += 1u;
+        if (left != node && left >= 0) pos += innerCount[left];
+        node = p;
+    }
+    order[i] = (int32_t)pos;
 }
 
 __global__ void k_ploc_depth(const uint32_t* __restrict__ height, uint32_t* __restrict__ maxDepth) {
@@ -461,15 +487,18 @@ __global__ void k_grid(const uint32_t* __restrict__ bounds, float* __restrict__ 
 
 __global__ void __launch_bounds__(256) k_emit_nodes(int n, const int32_t* __restrict__ children,
                                                     const float4* __restrict__ boxes,
-                                                    const float* __restrict__ grid, uint4* __restrict__ nodes) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n - 1) return;
-    const int32_t cl = children[2 * i], cr = children[2 * i + 1];
+                                                    const float* __restrict__ grid, const int32_t* __restrict__ order,
+                                                    uint4* __restrict__ nodes) {
+    const int src = blockIdx.x * blockDim.x + threadIdx.x;
+    if (src >= n - 1) return;
+    const int32_t cl = children[2 * src], cr = children[2 * src + 1];
     const int el = cl >= 0 ? cl : (n - 1 + ~cl), er = cr >= 0 ? cr : (n - 1 + ~cr);
     const float4 llo = boxes[2 * el], lhi = boxes[2 * el + 1];
     const float4 rlo = boxes[2 * er], rhi = boxes[2 * er + 1];
-    const int32_t pl = cl >= 0 ? cl : pack_leaf(~cl, 1);
-    const int32_t pr = cr >= 0 ? cr : pack_leaf(~cr, 1);
+    // `order` (optional) relabels inner nodes; the root keeps index 0
+    const int i = order ? order[src] : src;
+    const int32_t pl = cl >= 0 ? (order ? order[cl] : cl) : pack_leaf(~cl, 1);
+    const int32_t pr = cr >= 0 ? (order ? order[cr] : cr) : pack_leaf(~cr, 1);
     // outward rounding with a 1e-3 cell guard band against the rounding of the scaling itself
     auto qlo = [&](float v, int k) {
         const float c = floorf((v - grid[k]) * grid[3 + k] - 1e-3f);
@@ -544,6 +573,7 @@ cudaError_t build_lbvh(const BuildArgs& a, cudaStream_t st, uint64_t* launches) 
     } else {
         k_iota<<<1, 32, 0, st>>>(a.vals[0], n); L++;
     }
+    int32_t* order = nullptr;
     if (n >= 2 && a.use_ploc) {
         // scratch: the sort's second key/value buffers are free now
         int32_t* cluster[2] = {reinterpret_cast<int32_t*>(a.vals[1]), a.parent};
@@ -551,6 +581,8 @@ cudaError_t build_lbvh(const BuildArgs& a, cudaStream_t st, uint64_t* launches) 
         uint32_t* keep = a.flags;                         // n + 1 entries each (scan total in the last slot)
         uint32_t* merge = reinterpret_cast<uint32_t*>(a.keys[1]);
         uint32_t* height = a.nodeDepth;                   // 2n - 1 entries
+        int32_t* parentOf = reinterpret_cast<int32_t*>(a.centroid);     // centroids are dead after k_morton: 16n bytes
+        uint32_t* innerCount = reinterpret_cast<uint32_t*>(a.centroid) + n;
         k_ploc_init<<<nb(n, 256), 256, 0, st>>>(a.tris, a.vals[0], n, a.bounds, a.boxes, cluster[0], height); L++;
         int m = n, created = 0, cur = 0;
         uint32_t totals[2];
@@ -560,7 +592,7 @@ cudaError_t build_lbvh(const BuildArgs& a, cudaStream_t st, uint64_t* launches) 
             k_scan<<<1, 1024, 0, st>>>(keep, m); L++;
             k_scan<<<1, 1024, 0, st>>>(merge, m); L++;
             k_ploc_merge<<<nb(m, 256), 256, 0, st>>>(cluster[cur], nn, m, n, keep, merge, (n - 2) - created, a.boxes,
-                                                     a.children, height, cluster[cur ^ 1]); L++;
+                                                     a.children, height, parentOf, innerCount, cluster[cur ^ 1]); L++;
             cudaMemcpyAsync(&totals[0], keep + m, sizeof(uint32_t), cudaMemcpyDeviceToHost, st);
             cudaMemcpyAsync(&totals[1], merge + m, sizeof(uint32_t), cudaMemcpyDeviceToHost, st);
             cudaError_t e = cudaStreamSynchronize(st);
@@ -571,6 +603,10 @@ cudaError_t build_lbvh(const BuildArgs& a, cudaStream_t st, uint64_t* launches) 
             cur ^= 1;
         }
         k_ploc_depth<<<1, 32, 0, st>>>(height, a.maxDepth); L++;
+        if (a.dfs_layout) {
+            order = reinterpret_cast<int32_t*>(a.centroid) + 2 * (size_t)n;
+            k_dfs_order<<<nb(n - 1, 256), 256, 0, st>>>(n, a.children, parentOf, innerCount, order); L++;
+        }
     } else {
         if (n >= 2) {
             k_hierarchy<<<nb(n - 1, 256), 256, 0, st>>>(a.keys[0], n, a.children, a.parent); L++;
@@ -581,7 +617,7 @@ cudaError_t build_lbvh(const BuildArgs& a, cudaStream_t st, uint64_t* launches) 
                                             a.nodeDepth, a.maxDepth); L++;
     }
     k_grid<<<1, 32, 0, st>>>(a.bounds, a.grid); L++;
-    if (n >= 2) { k_emit_nodes<<<nb(n - 1, 256), 256, 0, st>>>(n, a.children, a.boxes, a.grid, a.nodes); L++; }
+    if (n >= 2) { k_emit_nodes<<<nb(n - 1, 256), 256, 0, st>>>(n, a.children, a.boxes, a.grid, order, a.nodes); L++; }
     k_emit_tris<<<nb(n, 256), 256, 0, st>>>(a.tris, a.vals[0], n, a.geom, a.shade, a.orig); L++;
     if (launches) *launches += L;
     return cudaGetLastError();

@@ -102,7 +102,7 @@ struct rt_ctx {
     int sm_count = 148;
     int extend_blocks_per_sm = 4;
     int leaf_vote = 8, refill = 8, node_steps = 3;
-    int use_ploc = 1;
+    int use_ploc = 1, dfs_layout = 1;
     cudaStream_t own_stream = nullptr;
     cudaStream_t stream = nullptr;
     std::string err;
@@ -461,6 +461,7 @@ int rt_create(rt_ctx** out, const rt_config* cfg) {
     // tuning knobs of the persistent traversal kernel (defaults chosen from ncu runs)
     if (const char* e1 = getenv("RT_EXT_LEAF_VOTE")) ctx->leaf_vote = std::max(1, std::min(32, atoi(e1)));
     if (const char* e2 = getenv("RT_EXT_REFILL")) ctx->refill = std::max(1, std::min(32, atoi(e2)));
+    if (const char* e6 = getenv("RT_BVH_LAYOUT")) ctx->dfs_layout = strcmp(e6, "creation") != 0;
     if (const char* e5 = getenv("RT_BVH_BUILDER")) ctx->use_ploc = strcmp(e5, "lbvh") != 0;
     if (const char* e4 = getenv("RT_EXT_NODE_STEPS")) ctx->node_steps = std::max(1, std::min(16, atoi(e4)));
     if (const char* e3 = getenv("RT_EXT_BLOCKS_PER_SM")) ctx->extend_blocks_per_sm = std::max(1, std::min(32, atoi(e3)));
@@ -583,6 +584,7 @@ int rt_scene_build(rt_ctx* ctx) {
     a.tris = ctx->d_tris.as<rt_triangle>();
     a.n = n;
     a.use_ploc = ctx->use_ploc;
+    a.dfs_layout = ctx->dfs_layout;
     a.centroid = ctx->d_centroid.as<float4>();
     a.bounds = ctx->d_bounds.as<uint32_t>();
     for (int i = 0; i < 2; i++) {

@@ -13,6 +13,7 @@ struct BuildArgs {
     const rt_triangle* tris;  // device copy of the caller's array (original order)
     int n;
     int use_ploc;             // 1 = PLOC hierarchy (default), 0 = Karras LBVH
+    int dfs_layout;           // 1 = store PLOC nodes in depth-first order
     float4* centroid;         // n
     uint32_t* bounds;         // 12 order-preserving uints
     uint64_t* keys[2];        // n each
