@@ -424,39 +424,57 @@ __device__ __forceinline__ BounceRandoms bounce_randoms(Rng<0>& rng, bool needDi
     return r;
 }
 // RT_RNG_PHILOX: draw j of a bounce is a pure function of (pixel, frame, sample, bounce, j), so the first
-// twelve draws (three Philox blocks = three rejection tries + the two extra draws after any of them) are
+// twenty draws (five Philox blocks = six rejection tries + the two extra draws after any of them) are
 // generated up front by the whole warp in lock step and the tries are evaluated with selects.  ncu on the
 // sequential version showed 9.5 of 32 lanes active per instruction in k_shade, most of it the divergent
-// rejection loop and the on-demand block generation.  Only the 11 % of lanes whose first three tries all
-// fail continue in the sequential loop (from draw 9).  Values and draw indices are identical to the
+// rejection loop and the on-demand block generation.  Only the 1.2 % of lanes whose first six tries all
+// fail continue in the sequential loop (from draw 18).  Values and draw indices are identical to the
 // sequential definition, so no bit of the image changes.
 __device__ __forceinline__ BounceRandoms bounce_randoms(Rng<1>& rng, bool needDir, int nExtra) {
-    uint32_t w[12];
-    philox4x32_10(0u, rng.bounce, rng.sample, 0x52543230u, rng.pixel, rng.frame, &w[0]);
-    philox4x32_10(1u, rng.bounce, rng.sample, 0x52543230u, rng.pixel, rng.frame, &w[4]);
-    philox4x32_10(2u, rng.bounce, rng.sample, 0x52543230u, rng.pixel, rng.frame, &w[8]);
-    float f[12];
+    constexpr int kBlocks = 5;            // 20 draws: six rejection tries (18) + the two draws after the last
+    constexpr int kTries = 6;             // P(all six fail) = 0.476^6 = 1.2 % of lanes take the sequential tail
+    float f[4 * kBlocks];
+    uint32_t lastBlock[4] = {0u, 0u, 0u, 0u};
 #pragma unroll
-    for (int i = 0; i < 12; i++) f[i] = u32_to_unit(w[i]);
+    for (int b = 0; b < kBlocks; b++) {
+        uint32_t w[4];
+        philox4x32_10((uint32_t)b, rng.bounce, rng.sample, 0x52543230u, rng.pixel, rng.frame, w);
+#pragma unroll
+        for (int k = 0; k < 4; k++) f[4 * b + k] = u32_to_unit(w[k]);
+        if (b == kBlocks - 1) {
+#pragma unroll
+            for (int k = 0; k < 4; k++) lastBlock[k] = w[k];
+        }
+    }
     BounceRandoms r;
     r.randDir = v3(0.0f, 0.0f, 0.0f);
     r.d0 = f[0];
     r.d1 = f[1];
     if (needDir) {
-        const V3 c1 = v3(f[0] * 2.0f - 1.0f, f[1] * 2.0f - 1.0f, f[2] * 2.0f - 1.0f);
-        const V3 c2 = v3(f[3] * 2.0f - 1.0f, f[4] * 2.0f - 1.0f, f[5] * 2.0f - 1.0f);
-        const V3 c3 = v3(f[6] * 2.0f - 1.0f, f[7] * 2.0f - 1.0f, f[8] * 2.0f - 1.0f);
-        const bool a1 = length(c1) < 1.0f, a2 = length(c2) < 1.0f, a3 = length(c3) < 1.0f;
-        if (a1 || a2 || a3) {
-            const V3 c = a1 ? c1 : (a2 ? c2 : c3);
+        // all tries evaluated in lock step; the FIRST accepted one wins, exactly as the sequential loop
+        bool found = false;
+        V3 c = v3(0.0f, 0.0f, 0.0f);
+        float d0 = 0.0f, d1 = 0.0f;
+#pragma unroll
+        for (int t = 0; t < kTries; t++) {
+            const V3 cand = v3(f[3 * t] * 2.0f - 1.0f, f[3 * t + 1] * 2.0f - 1.0f, f[3 * t + 2] * 2.0f - 1.0f);
+            const bool acc = !found && length(cand) < 1.0f;
+            if (acc) {
+                c = cand;
+                d0 = f[3 * t + 3];
+                d1 = f[3 * t + 4];
+            }
+            found = found || acc;
+        }
+        if (found) {
             r.randDir = normalize(c);
-            r.d0 = a1 ? f[3] : (a2 ? f[6] : f[9]);
-            r.d1 = a1 ? f[4] : (a2 ? f[7] : f[10]);
+            r.d0 = d0;
+            r.d1 = d1;
         } else {
-            // tries 4..100 of S:176-183, sequentially, starting at draw 9 (block 2 is already in hand)
-            rng.j = 9u;
-            rng.cache[0] = w[8]; rng.cache[1] = w[9]; rng.cache[2] = w[10]; rng.cache[3] = w[11];
-            for (int i = 3; i < 100; i++) {
+            // tries 7..100 of S:176-183, sequentially, from draw 18 (the last block is already in hand)
+            rng.j = 3u * kTries;
+            rng.cache[0] = lastBlock[0]; rng.cache[1] = lastBlock[1]; rng.cache[2] = lastBlock[2]; rng.cache[3] = lastBlock[3];
+            for (int i = kTries; i < 100; i++) {
                 const float x = rng.next() * 2.0f - 1.0f;
                 const float y = rng.next() * 2.0f - 1.0f;
                 const float z = rng.next() * 2.0f - 1.0f;
