@@ -101,8 +101,8 @@ struct rt_ctx {
     rt_config cfg{};
     int sm_count = 148;
     int extend_blocks_per_sm = 4;
-    int leaf_vote = 8, refill = 8, node_steps = 3;
-    int use_ploc = 1, dfs_layout = 1;
+    int leaf_vote = 12, refill = 8, node_steps = 3;
+    int use_ploc = 1, dfs_layout = 1, speculative = 1;
     cudaStream_t own_stream = nullptr;
     cudaStream_t stream = nullptr;
     std::string err;
@@ -183,6 +183,7 @@ Launcher make_launcher(rt_ctx* ctx) {
     L.leaf_vote = ctx->leaf_vote;
     L.refill = ctx->refill;
     L.node_steps = ctx->node_steps;
+    L.speculative = ctx->speculative != 0;
     L.kernel_launches = &ctx->kernel_launches;
     L.extend_launches = &ctx->extend_launches;
     L.ev_pool = ctx->events.data();
@@ -461,6 +462,7 @@ int rt_create(rt_ctx** out, const rt_config* cfg) {
     // tuning knobs of the persistent traversal kernel (defaults chosen from ncu runs)
     if (const char* e1 = getenv("RT_EXT_LEAF_VOTE")) ctx->leaf_vote = std::max(1, std::min(32, atoi(e1)));
     if (const char* e2 = getenv("RT_EXT_REFILL")) ctx->refill = std::max(1, std::min(32, atoi(e2)));
+    if (const char* e7 = getenv("RT_EXT_SPEC")) ctx->speculative = atoi(e7);
     if (const char* e6 = getenv("RT_BVH_LAYOUT")) ctx->dfs_layout = strcmp(e6, "creation") != 0;
     if (const char* e5 = getenv("RT_BVH_BUILDER")) ctx->use_ploc = strcmp(e5, "lbvh") != 0;
     if (const char* e4 = getenv("RT_EXT_NODE_STEPS")) ctx->node_steps = std::max(1, std::min(16, atoi(e4)));

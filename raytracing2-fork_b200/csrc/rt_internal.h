@@ -74,6 +74,7 @@ struct Launcher {
     int leaf_vote;     // k_extend: leaf step when this many lanes wait at a leaf
     int refill;        // k_extend: refill when this many lanes are idle
     int node_steps;    // k_extend: node steps per vote
+    bool speculative;  // k_extend: postponed-leaf variant
     uint64_t* kernel_launches;
     uint64_t* extend_launches;
     // optional per-class device timing

@@ -285,7 +285,15 @@ __device__ __forceinline__ void node_step(const SceneView& sc, const RayRegs& r,
     node = (hitL || hitR) ? nearC : kPop;
 }
 
-template <bool COUNT>
+constexpr int32_t kDrain = (int32_t)0x80000002;     // lane state (SPEC): stack empty, a postponed leaf still to test
+constexpr int32_t kNoLeaf = (int32_t)0x80000003;    // `post` holds no leaf
+__device__ __forceinline__ bool is_leaf_code(int32_t x) { return x < 0 && (uint32_t)x > (uint32_t)kNoLeaf; }
+
+// SPEC = speculative traversal (Aila & Laine's "postponed leaf"): a lane that reaches a leaf parks it in
+// `post` and keeps descending; it only has to wait for a leaf step when it reaches a SECOND leaf (or runs
+// out of nodes).  Node steps then run with more lanes, leaf steps test up to two leaves per lane; the price
+// is a stale bestT while a leaf is parked (a few more node visits).  Selected at run time (RT_EXT_SPEC).
+template <bool COUNT, bool SPEC>
 __global__ void __launch_bounds__(kExtBlock) k_extend(const __grid_constant__ SceneView sc, PathArrays cur,
                                                       float4* __restrict__ hit, const uint32_t* __restrict__ count,
                                                       uint32_t* __restrict__ cursor, ExtendTune tune,
@@ -309,6 +317,7 @@ __global__ void __launch_bounds__(kExtBlock) k_extend(const __grid_constant__ Sc
     float bestU = 0, bestV = 0;
     int32_t bestSlot = -1, bestOrig = 0x7fffffff;
     int32_t node = kIdle;
+    int32_t post = kNoLeaf;
     int sp = 0;
     uint32_t visits = 0, tests = 0;
 
@@ -317,18 +326,53 @@ __global__ void __launch_bounds__(kExtBlock) k_extend(const __grid_constant__ Sc
             hit[i] = make_float4(kMissT, 0.0f, 0.0f, __int_as_float(-1));
     }
 
+    // exact Möller–Trumbore against every triangle of one leaf; min (dst, original index) wins
+    auto test_leaf = [&](int32_t code) {
+        const int32_t packed = ~code;
+        const int32_t first = packed & kLeafFirstMask;
+        const int32_t cnt = (packed >> kLeafCountShift) + 1;
+        for (int32_t s = first; s < first + cnt; s++) {
+            const TriGeom tg = load_tri(sc, s);
+            if (COUNT) tests++;
+            float dst, u, v;
+            if (ray_triangle(r.o, r.d, tg.a, tg.e0, tg.e1, tg.N, dst, u, v)) {
+                if (dst <= r.bestT && dst < kMissT) {
+                    const int32_t orig = __ldg(&sc.tri_orig[s]);
+                    if (dst < r.bestT || orig < bestOrig) {
+                        r.bestT = dst; bestU = u; bestV = v; bestSlot = s; bestOrig = orig;
+                    }
+                }
+            }
+        }
+    };
+    // one stack entry; entries that can no longer hold a hit are dropped
+    auto pop_one = [&]() {
+        --sp;
+        float tn;
+        int32_t c;
+        st.get(sp, c, tn);
+        if (tn <= r.bestT * kWiden) node = c;
+    };
+    auto postpone = [&]() {
+        if (SPEC && is_leaf_code(node) && post == kNoLeaf) {
+            post = node;
+            node = kPop;
+        }
+    };
+
     for (;;) {
         // ---- pop phase: lanes that finished a subtree take the next one that can still hold a hit
         if (node == kPop) {
             if (sp == 0) {
-                hit[ray] = make_float4(r.bestT, bestU, bestV, __int_as_float(bestSlot));
-                node = kIdle;
+                if (SPEC && post != kNoLeaf) {
+                    node = kDrain;
+                } else {
+                    hit[ray] = make_float4(r.bestT, bestU, bestV, __int_as_float(bestSlot));
+                    node = kIdle;
+                }
             } else {
-                --sp;
-                float tn;
-                int32_t c;
-                st.get(sp, c, tn);
-                if (tn <= r.bestT * kWiden) node = c;
+                pop_one();
+                postpone();
             }
         }
         // ---- refill idle lanes from the queue
@@ -350,7 +394,9 @@ __global__ void __launch_bounds__(kExtBlock) k_extend(const __grid_constant__ Sc
                     r.g = make_grid_ray(sc, r.o, r.d);
                     r.bestT = kMissT; bestU = 0.0f; bestV = 0.0f; bestSlot = -1; bestOrig = 0x7fffffff;
                     sp = 0;
+                    post = kNoLeaf;
                     node = sc.root_is_leaf ? pack_leaf(0, sc.num_tris) : 0;
+                    postpone();
                 }
             }
             if (base + want >= n) exhausted = true;
@@ -361,35 +407,33 @@ __global__ void __launch_bounds__(kExtBlock) k_extend(const __grid_constant__ Sc
             continue;
         }
         // ---- vote: leaf step or node steps (warp-uniform branch)
-        const uint32_t leafM = __ballot_sync(FULL, node < 0 && node != kPop && node != kIdle);
-        const uint32_t nodeM = __ballot_sync(FULL, node >= 0);
-        if ((int)__popc(leafM) >= tune.leafVote || nodeM == 0u) {
-            if (node < 0 && node != kPop && node != kIdle) {
-                const int32_t packed = ~node;
-                const int32_t first = packed & kLeafFirstMask;
-                const int32_t cnt = (packed >> kLeafCountShift) + 1;
-                for (int32_t s = first; s < first + cnt; s++) {
-                    const TriGeom tg = load_tri(sc, s);
-                    if (COUNT) tests++;
-                    float dst, u, v;
-                    if (ray_triangle(r.o, r.d, tg.a, tg.e0, tg.e1, tg.N, dst, u, v)) {
-                        if (dst <= r.bestT && dst < kMissT) {
-                            const int32_t orig = __ldg(&sc.tri_orig[s]);
-                            if (dst < r.bestT || orig < bestOrig) {
-                                r.bestT = dst; bestU = u; bestV = v; bestSlot = s; bestOrig = orig;
-                            }
-                        }
-                    }
+        const bool parked = is_leaf_code(node) || node == kDrain;
+        const uint32_t parkedM = __ballot_sync(FULL, parked);
+        const uint32_t nodeM = __ballot_sync(FULL, node >= 0 || (SPEC && node == kPop));
+        if ((int)__popc(parkedM) >= tune.leafVote || nodeM == 0u) {
+            if (SPEC) {
+                if (post != kNoLeaf) {
+                    test_leaf(post);
+                    post = kNoLeaf;
+                    if (is_leaf_code(node)) test_leaf(node);
+                    if (parked) node = kPop;
                 }
+            } else if (parked) {
+                test_leaf(node);
                 node = kPop;
             }
         } else {
-            // several node steps per vote amortise the voting overhead (lanes that reach a leaf wait)
+            // several node steps per vote amortise the voting overhead
 #pragma unroll 1
             for (int k = 0; k < tune.nodeSteps; k++) {
+                if (SPEC && node == kPop && sp > 0) {
+                    pop_one();
+                    postpone();
+                }
                 if (node >= 0) {
                     if (COUNT) visits++;
                     node_step(sc, r, node, sp, st);
+                    postpone();
                 }
             }
         }
@@ -863,8 +907,8 @@ struct Timed {
 int wf_extend_blocks_per_sm(bool instrument) {
     int nb = 0;
     cudaError_t e = instrument
-        ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_extend<true>, kExtBlock, 0)
-        : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_extend<false>, kExtBlock, 0);
+        ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_extend<true, false>, kExtBlock, 0)
+        : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_extend<false, false>, kExtBlock, 0);
     return e == cudaSuccess && nb > 0 ? nb : 4;
 }
 
@@ -903,9 +947,11 @@ cudaError_t wf_render_batch(const Launcher& L, const SceneView& sc, const WaveBu
         {
             Timed t(L, 0);
             if (L.instrument)
-                k_extend<true><<<extGrid, kExtBlock, 0, L.st>>>(sc, a, wb.hit, wb.counts + bounce, cursors + bounce, tune, wb.stats);
+                k_extend<true, false><<<extGrid, kExtBlock, 0, L.st>>>(sc, a, wb.hit, wb.counts + bounce, cursors + bounce, tune, wb.stats);
+            else if (L.speculative)
+                k_extend<false, true><<<extGrid, kExtBlock, 0, L.st>>>(sc, a, wb.hit, wb.counts + bounce, cursors + bounce, tune, wb.stats);
             else
-                k_extend<false><<<extGrid, kExtBlock, 0, L.st>>>(sc, a, wb.hit, wb.counts + bounce, cursors + bounce, tune, wb.stats);
+                k_extend<false, false><<<extGrid, kExtBlock, 0, L.st>>>(sc, a, wb.hit, wb.counts + bounce, cursors + bounce, tune, wb.stats);
             (*L.kernel_launches)++;
             (*L.extend_launches)++;
         }
