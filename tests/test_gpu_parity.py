@@ -423,3 +423,69 @@ def test_config4_scale_mesh_properties():
         acc += b2.screenshot_partial(u, 2)
         b2.close()
     assert np.array_equal(acc, total)
+
+
+def test_gpu_against_committed_goldens():
+    """Oracle-free anchor: the fixtures in tests/golden/ were minted once from the oracle (make_golden.py) and
+    are committed; the GPU must reproduce them without the oracle library being involved at all."""
+    import json, os, zlib
+    golden = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    meta = json.load(open(os.path.join(golden, "golden.json")))
+    crc = lambda a: zlib.crc32(np.ascontiguousarray(a).tobytes()) & 0xffffffff
+    scene = rt.scene_classic_cornell()
+    cam = rt.make_camera(512, 512, (0.0, 0.0, 15.5))
+    u = rt.screenshot_uniforms(scene, cam, spp=64, max_bounce=8, env_light=False)
+    cam64 = rt.make_camera(64, 64, (0.0, 0.0, 15.5))
+    u64 = rt.screenshot_uniforms(scene, cam64, spp=8, max_bounce=8, env_light=False)
+    for mode, name in ((rt.RNG_REF_PCG, "pcg"), (rt.RNG_PHILOX, "philox")):
+        be = backend(scene, rng_mode=mode)
+        tri, dst = be.first_hit(u, rt.FIRST_HIT_CENTRE)
+        assert crc(tri) == meta["config1_first_hit_centre_crc"] and crc(dst) == meta["config1_first_hit_centre_dst_crc"]
+        tri, _ = be.first_hit(u, rt.FIRST_HIT_SAMPLE0)
+        assert crc(tri) == meta[f"config1_first_hit_sample0_{name}_crc"]
+        tri64, _ = be.first_hit(u64, rt.FIRST_HIT_CENTRE)
+        assert np.array_equal(tri64, np.load(os.path.join(golden, "classic_first_hit_64.npy")))
+        be.render_frame(u64)
+        assert crc(be.read_frame()) == meta[f"classic_frame_64_{name}_crc"]
+        assert np.array_equal(be.screenshot(u64, 2), np.load(os.path.join(golden, f"classic_shot_64_{name}.npy")))
+        be.close()
+    s2 = rt.scene_textured_sphere(n_quads=224, container="cornell", tex_size=256)
+    cam2 = rt.camera_for_box(s2, 240, 135)
+    u2 = rt.screenshot_uniforms(s2, cam2, spp=4, max_bounce=6, env_light=False)
+    be = backend(s2)
+    t2, d2 = be.first_hit(u2, rt.FIRST_HIT_CENTRE)
+    assert crc(t2) == meta["config2_first_hit_240x135_crc"] and crc(d2) == meta["config2_first_hit_240x135_dst_crc"]
+
+
+def test_config1_full_size_screenshot_properties(classic):
+    """BASELINE config 1 at its full size (512x512, 64 spp, depth 8, one frame) in both RNG modes: the two
+    generators must give statistically the same picture (they are different streams, so PSNR not bits), the
+    image must be independent of the path budget, and the Philox frame must equal the oracle's on a crop."""
+    scene, orc = classic
+    cam = rt.make_camera(512, 512, (0.0, 0.0, 15.5))
+    u = rt.screenshot_uniforms(scene, cam, spp=64, max_bounce=8, env_light=False)
+    imgs = {}
+    for mode in (rt.RNG_REF_PCG, rt.RNG_PHILOX):
+        be = backend(scene, rng_mode=mode)
+        be.render_frame(u)
+        imgs[mode] = be.read_frame()[..., :3]
+        if mode == rt.RNG_PHILOX:
+            u1 = u.copy()
+            u1["frameIndex"] = 1
+            be.render_frame(u1)
+            other_philox = be.read_frame()[..., :3]
+        be.close()
+    # tolerance: the reference-stream image may differ from the Philox image by no more than two independent
+    # Philox estimates (frame 0 vs frame 1) differ from each other, + 1.5 dB, on 8x8 box-filtered images
+    def pool(a):
+        return a.reshape(64, 8, 64, 8, 3).mean(axis=(1, 3))
+    noise_floor = psnr(pool(other_philox), pool(imgs[rt.RNG_PHILOX]))
+    assert psnr(pool(imgs[rt.RNG_REF_PCG]), pool(imgs[rt.RNG_PHILOX])) > noise_floor - 1.5
+    assert noise_floor > 20.0
+    be = backend(scene, max_paths_in_flight=512 * 512 * 5)
+    be.render_frame(u)
+    assert_image_equal(be.read_frame()[..., :3], imgs[rt.RNG_PHILOX], "path budget independence at 512^2")
+    region = (224, 200, 288, 232)   # 64x32 crop through the tall box and the back wall
+    ref = orc.render_frame(u, rng_mode=rt.RNG_PHILOX, region=region)
+    x0, y0, x1, y1 = region
+    assert_image_equal(imgs[rt.RNG_PHILOX][y0:y1, x0:x1], ref[y0:y1, x0:x1, :3], "config 1 crop vs oracle")
