@@ -44,6 +44,7 @@ OTHER_WORKLOADS = {
     "config1": dict(width=512, height=512, frames=1, max_bounce=8),
     "config3": dict(width=1920, height=1080, frames=8, max_bounce=16),
     "config4": dict(width=3840, height=2160, frames=16, max_bounce=8),
+    "config2_robot": dict(width=1920, height=1080, frames=4, max_bounce=20),   # needs tools/make_assets.sh
 }
 
 
@@ -54,6 +55,9 @@ def build_workload(rt, width, height):
         cam = rt.make_camera(width, height, (0.0, 0.0, 15.5))
     elif name == "config3":
         scene = rt.scene_textured_sphere(n_quads=WORKLOAD["n_quads"], container="mirror", tex_size=WORKLOAD["tex_size"])
+        cam = rt.camera_for_box(scene, width, height)
+    elif name == "config2_robot":
+        scene = rt.scene_from_rtsc(os.path.join(REPO, "assets", "_gen", "robot.rtsc"), container="cornell")
         cam = rt.camera_for_box(scene, width, height)
     elif name == "config4":
         scene = rt.scene_big_sphere(n_quads=2236)
@@ -393,7 +397,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--frames", type=int, default=0, help="frames per GPU (default 4 = 256 spp)")
-    ap.add_argument("--workload", default="config2", choices=["config1", "config2", "config3", "config4"],
+    ap.add_argument("--workload", default="config2", choices=["config1", "config2", "config3", "config4", "config2_robot"],
                     help="BASELINE config to measure (default and contract: config2)")
     ap.add_argument("--split", default="frames", choices=["frames", "tiles"],
                     help="N > 1: frame-slice split + ncclReduce (default) or image-tile split + gather")

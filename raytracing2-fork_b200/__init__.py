@@ -547,6 +547,23 @@ def scene_textured_sphere(n_quads=224, container="cornell", tex_size=1024) -> Sc
     return s
 
 
+def scene_from_rtsc(path: str, container="cornell") -> Scene:
+    """A model written by the reference's loader (tools/make_assets.sh → assets/_gen/<model>.rtsc: triangles,
+    the material table INCLUDING the five fixed materials, decoded textures) inside a reference container —
+    config 2(i)/3(i) with `Data/robot`."""
+    d = defaults()
+    s = Scene()
+    s.load(path)
+    n = s.materials.size
+    if container == "cornell":
+        s.add_cornell_box(d.cornell_light_size, d.cornell_padding, n - 2, True)
+    elif container == "mirror":
+        s.add_mirror_cornell_box(d.cornell_light_size, d.cornell_padding, n - 2, n - 1)
+    elif container != "none":
+        raise ValueError(container)
+    return s
+
+
 def scene_big_sphere(n_quads=2236) -> Scene:
     """Config 4: 2·n² ≈ 10 M-triangle diffuse displaced sphere in the classic Cornell room
     (walls + light, without the two cubes)."""
