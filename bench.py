@@ -192,8 +192,8 @@ def workload_config(n_gpus):
         "rng": "philox4x32-10 keyed (pixel, frame, sample, bounce, draw)",
         "frames_total": WORKLOAD["frames"] * n_gpus,
         "split": "none" if n_gpus == 1 else "frame-slice (f % N == rank) + ncclReduce of the 8-bit frame sums to rank 0",
-        "cache": "path state of one batch (8.3 M paths x 128 B = 1.06 GB) is larger than L2; the 11 MB BVH is "
-                 "L2-resident by nature of the workload; no explicit flush",
+        "cache": "path state of one batch (64 samples x 2.07 M pixels = 133 M paths x 128 B = 17 GB) is far larger than "
+                 "L2; the 10 MB BVH is L2-resident by nature of the workload; no explicit flush",
     }
 
 

@@ -103,6 +103,7 @@ struct rt_ctx {
     int extend_blocks_per_sm = 4;
     int leaf_vote = 12, refill = 8, node_steps = 3;
     int use_ploc = 1, dfs_layout = 1, speculative = 1;
+    uint64_t default_budget = (uint64_t)128 << 20;  // path slots in flight (128 B each = 16 GiB; capped by free memory)
     cudaStream_t own_stream = nullptr;
     cudaStream_t stream = nullptr;
     std::string err;
@@ -270,7 +271,7 @@ int prepare_image(rt_ctx* ctx, int W, int H) {
 
 int lanes_for(rt_ctx* ctx, size_t P, int spp) {
     if (ctx->cfg.rng_mode == RT_RNG_REF_PCG) return 1;  // the reference stream is sequential per pixel
-    const uint64_t budget = ctx->cfg.max_paths_in_flight ? ctx->cfg.max_paths_in_flight : (uint64_t)16 << 20;
+    uint64_t budget = ctx->cfg.max_paths_in_flight ? ctx->cfg.max_paths_in_flight : ctx->default_budget;
     uint64_t lanes = P ? budget / P : 1;
     if (lanes < 1) lanes = 1;
     if (lanes > (uint64_t)spp) lanes = (uint64_t)spp;
@@ -459,9 +460,19 @@ int rt_create(rt_ctx** out, const rt_config* cfg) {
     }
     ctx->stream = ctx->own_stream;
     ctx->extend_blocks_per_sm = wf_extend_blocks_per_sm(cfg->instrument != 0);
+    {
+        // Path slots: fewer, larger wavefronts amortise the drain of the persistent kernels (config 2: 8 lanes
+        // per pixel 1203 ms/step, 64 lanes 1057 ms).  HBM is there to be used: default 128 Mi slots = 16 GiB,
+        // never more than 40 % of what is free.
+        size_t freeB = 0, totalB = 0;
+        if (cudaMemGetInfo(&freeB, &totalB) == cudaSuccess && freeB > 0)
+            ctx->default_budget = std::min<uint64_t>(ctx->default_budget, (uint64_t)(freeB * 0.4) / 128u);
+        if (ctx->default_budget < (1u << 20)) ctx->default_budget = 1u << 20;
+    }
     // tuning knobs of the persistent traversal kernel (defaults chosen from ncu runs)
     if (const char* e1 = getenv("RT_EXT_LEAF_VOTE")) ctx->leaf_vote = std::max(1, std::min(32, atoi(e1)));
     if (const char* e2 = getenv("RT_EXT_REFILL")) ctx->refill = std::max(1, std::min(32, atoi(e2)));
+    if (const char* e8 = getenv("RT_MAX_PATHS_MI")) ctx->default_budget = (uint64_t)std::max(1, atoi(e8)) << 20;
     if (const char* e7 = getenv("RT_EXT_SPEC")) ctx->speculative = atoi(e7);
     if (const char* e6 = getenv("RT_BVH_LAYOUT")) ctx->dfs_layout = strcmp(e6, "creation") != 0;
     if (const char* e5 = getenv("RT_BVH_BUILDER")) ctx->use_ploc = strcmp(e5, "lbvh") != 0;
