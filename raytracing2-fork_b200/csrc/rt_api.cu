@@ -101,7 +101,7 @@ struct rt_ctx {
     rt_config cfg{};
     int sm_count = 148;
     int extend_blocks_per_sm = 4;
-    int leaf_vote = 12, refill = 8, node_steps = 3;
+    int leaf_vote = 12, refill = 8, node_steps = 4;
     int use_ploc = 1, dfs_layout = 1, speculative = 1;
     uint64_t default_budget = (uint64_t)128 << 20;  // path slots in flight (128 B each = 16 GiB; capped by free memory)
     cudaStream_t own_stream = nullptr;
