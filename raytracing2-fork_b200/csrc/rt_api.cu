@@ -80,6 +80,7 @@ struct DevBuf {
         cap = 0;
         cudaError_t e = cudaMalloc(&p, bytes ? bytes : 16);
         if (e == cudaSuccess) cap = bytes;
+        else cudaGetLastError();  // a failed allocation is reported once (RT_ERR_OOM), not again by the next launch check
         return e;
     }
     void release() {
@@ -102,7 +103,7 @@ struct rt_ctx {
     int sm_count = 148;
     int extend_blocks_per_sm = 4;
     int leaf_vote = 12, refill = 8, node_steps = 4;
-    int use_ploc = 1, dfs_layout = 1, speculative = 1;
+    int use_ploc = 1, dfs_layout = 1, speculative = 1, shade_blocks_per_sm = 64;
     uint64_t default_budget = (uint64_t)128 << 20;  // path slots in flight (128 B each = 16 GiB; capped by free memory)
     cudaStream_t own_stream = nullptr;
     cudaStream_t stream = nullptr;
@@ -185,6 +186,7 @@ Launcher make_launcher(rt_ctx* ctx) {
     L.refill = ctx->refill;
     L.node_steps = ctx->node_steps;
     L.speculative = ctx->speculative != 0;
+    L.shade_blocks_per_sm = ctx->shade_blocks_per_sm;
     L.kernel_launches = &ctx->kernel_launches;
     L.extend_launches = &ctx->extend_launches;
     L.ev_pool = ctx->events.data();
@@ -472,6 +474,7 @@ int rt_create(rt_ctx** out, const rt_config* cfg) {
     // tuning knobs of the persistent traversal kernel (defaults chosen from ncu runs)
     if (const char* e1 = getenv("RT_EXT_LEAF_VOTE")) ctx->leaf_vote = std::max(1, std::min(32, atoi(e1)));
     if (const char* e2 = getenv("RT_EXT_REFILL")) ctx->refill = std::max(1, std::min(32, atoi(e2)));
+    if (const char* e9 = getenv("RT_SHADE_BLOCKS_PER_SM")) ctx->shade_blocks_per_sm = std::max(1, std::min(256, atoi(e9)));
     if (const char* e8 = getenv("RT_MAX_PATHS_MI")) ctx->default_budget = (uint64_t)std::max(1, atoi(e8)) << 20;
     if (const char* e7 = getenv("RT_EXT_SPEC")) ctx->speculative = atoi(e7);
     if (const char* e6 = getenv("RT_BVH_LAYOUT")) ctx->dfs_layout = strcmp(e6, "creation") != 0;

@@ -75,6 +75,7 @@ struct Launcher {
     int refill;        // k_extend: refill when this many lanes are idle
     int node_steps;    // k_extend: node steps per vote
     bool speculative;  // k_extend: postponed-leaf variant
+    int shade_blocks_per_sm;  // grid-stride k_shade: blocks per SM
     uint64_t* kernel_launches;
     uint64_t* extend_launches;
     // optional per-class device timing

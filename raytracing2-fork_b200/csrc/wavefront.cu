@@ -937,8 +937,8 @@ cudaError_t wf_render_batch(const Launcher& L, const SceneView& sc, const WaveBu
         (*L.kernel_launches)++;
     }
     // fixed-size grids that read the live count on the device: no host round trip per bounce
-    const int grid = (int)((n + kBlock - 1) / kBlock < (long long)L.sm_count * 8 ? (n + kBlock - 1) / kBlock
-                                                                                : (long long)L.sm_count * 8);
+    const long long gridCap = (long long)L.sm_count * L.shade_blocks_per_sm;
+    const int grid = (int)((n + kBlock - 1) / kBlock < gridCap ? (n + kBlock - 1) / kBlock : gridCap);
     const int extGrid = L.extend_grid;
     uint32_t* cursors = wb.counts + ncounts;
     ExtendTune tune{L.leaf_vote, L.refill, L.node_steps};
