@@ -39,7 +39,7 @@ const uint8_t* rth_scene_texture(const rth_scene* s, int32_t slot, int32_t* w, i
 
 /* model folder ----------------------------------------------------------------------------------
  * getTrianglesData_(folder, …) of mesh.h:279-613: first .obj of the folder, every .mtl, textures/
- * (PNG decoded here; JPEG not yet).  Fills triangles, the material table in the reference's std::map
+ * (PNG and baseline 4:4:4 JPEG decoded here, byte-identical to stb_image).  Fills triangles, the material table in the reference's std::map
  * order, and up to 5 textures (flipped vertically like stbi_set_flip_vertically_on_load(true)).
  * The scene must be fresh.  Follow with rth_add_fixed_materials + a container, as main() does. */
 int rth_load_model_folder(rth_scene* s, const char* folder);

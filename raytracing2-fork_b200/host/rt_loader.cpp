@@ -18,8 +18,8 @@
 //   * the .obj used is the first one of the (sorted) listing (M:223-253).
 // Differences, on purpose: fields the reference leaves uninitialised (UVs of untextured faces,
 // unused Material floats, RTXTriangle.pad) are zero; errors are returned, not thrown as ints.
-// JPEG textures are not decoded yet (round 2) — such folders load through an RTSC file written by
-// oracle/_ref/ref_host, which runs the reference's loader and stb.
+// Textures: PNG (all colour types, non-interlaced) and baseline JPEG without chroma subsampling — every
+// texture the reference ships.
 #include <zlib.h>
 
 #include <algorithm>
@@ -190,18 +190,313 @@ bool decodePng(const std::vector<uint8_t>& file, Image& out, std::string& err) {
     return true;
 }
 
+// ------------------------------------------------------------------------------------------------ JPEG
+// Baseline sequential JPEG (SOF0, 8 bit, Huffman), 1 or 3 components without chroma subsampling — which is
+// what every JPEG the reference ships is (RayTracing/Data/{robot,plants,toonHouse}/textures).  The reference
+// decodes through stb_image 2.30 (external/stb, public domain); JPEG decoding is only specified up to the
+// accuracy of the IDCT and of the colour conversion, so to hand the SAME texels to the renderer this decoder
+// restates the arithmetic stb_image uses for those two steps: the Loeffler–Ligtenberg–Moschytz integer IDCT
+// with 12-bit constants (column pass >> 10 after +512, row pass >> 17 after +65536 + (128 << 17)) and the
+// 20-bit fixed-point YCbCr → RGB conversion.  tests/test_loader_cpu.py compares the result byte for byte
+// with the reference's own loader.  Subsampled or progressive files are rejected with an error.
+struct JpegDecoder {
+    const uint8_t* d;
+    size_t n, pos = 0;
+    std::string err;
+    int W = 0, H = 0, ncomp = 0;
+    struct Comp { int id = 0, h = 1, v = 1, tq = 0, td = 0, ta = 0, pred = 0; } comp[3];
+    uint16_t qt[4][64] = {};
+    struct Huff {
+        bool present = false;
+        uint8_t size[257];
+        uint16_t code[256];
+        uint8_t val[256];
+        int maxcode[18];
+        int delta[17];
+        int count = 0;
+    } huff[2][4];
+    int restart = 0;
+    uint32_t bitbuf = 0;
+    int bitcnt = 0;
+    bool hitMarker = false;
+    uint8_t marker = 0;
+
+    JpegDecoder(const uint8_t* data, size_t len) : d(data), n(len) {}
+    bool fail(const char* m) { if (err.empty()) err = m; return false; }
+    int u8() { return pos < n ? d[pos++] : 0; }
+    int u16() { const int a = u8(); return a << 8 | u8(); }
+
+    bool buildHuff(Huff& h, const uint8_t counts[16]) {
+        int k = 0;
+        for (int i = 0; i < 16; i++)
+            for (int j = 0; j < counts[i]; j++) h.size[k++] = (uint8_t)(i + 1);
+        h.size[k] = 0;
+        h.count = k;
+        int code = 0;
+        k = 0;
+        for (int j = 1; j <= 16; j++) {
+            h.delta[j] = k - code;
+            if (h.size[k] == j) {
+                while (h.size[k] == j) h.code[k++] = (uint16_t)code++;
+                if (code - 1 >= (1 << j)) return fail("bad JPEG code lengths");
+            }
+            h.maxcode[j] = code << (16 - j);
+            code <<= 1;
+        }
+        h.maxcode[17] = 0x7fffffff;
+        h.present = true;
+        return true;
+    }
+    void fill() {
+        while (bitcnt <= 24) {
+            int b = 0;
+            if (!hitMarker) {
+                b = pos < n ? d[pos++] : 0;
+                if (b == 0xff) {
+                    int c = pos < n ? d[pos++] : 0;
+                    while (c == 0xff) c = pos < n ? d[pos++] : 0;
+                    if (c != 0) {
+                        marker = (uint8_t)c;
+                        hitMarker = true;
+                        b = 0;
+                    }
+                }
+            }
+            bitbuf |= (uint32_t)b << (24 - bitcnt);
+            bitcnt += 8;
+        }
+    }
+    int decodeSym(const Huff& h) {
+        if (bitcnt < 16) fill();
+        const int top = (int)(bitbuf >> 16);
+        int len = 1;
+        while (len <= 16 && top >= h.maxcode[len]) len++;
+        if (len > 16 || len > bitcnt) return -1;
+        const int idx = (int)((bitbuf >> (32 - len)) & ((1u << len) - 1u)) + h.delta[len];
+        if (idx < 0 || idx >= h.count) return -1;
+        bitbuf <<= len;
+        bitcnt -= len;
+        return h.val[idx];
+    }
+    int receiveExtend(int nb) {
+        if (nb == 0) return 0;
+        if (bitcnt < nb) fill();
+        const int v = (int)(bitbuf >> (32 - nb));
+        bitbuf <<= nb;
+        bitcnt -= nb;
+        return v < (1 << (nb - 1)) ? v - (1 << nb) + 1 : v;  // EXTEND of ITU T.81 F.2.2.1
+    }
+    static uint8_t clamp8(int x) { return (uint8_t)(x < 0 ? 0 : (x > 255 ? 255 : x)); }
+
+    // LL&M integer IDCT, 12-bit constants; data in natural order, already dequantised
+    static void idct(uint8_t* out, int stride, const short data[64]) {
+        auto f2f = [](double x) { return (int)(x * 4096 + 0.5); };
+        static const int c0541 = f2f(0.5411961), c1847 = f2f(-1.847759065), c0765 = f2f(0.765366865),
+                         c1175 = f2f(1.175875602), c0298 = f2f(0.298631336), c2053 = f2f(2.053119869),
+                         c3072 = f2f(3.072711026), c1501 = f2f(1.501321110), c0899 = f2f(-0.899976223),
+                         c2562 = f2f(-2.562915447), c1961 = f2f(-1.961570560), c0390 = f2f(-0.390180644);
+        auto pass = [&](int s0, int s1, int s2, int s3, int s4, int s5, int s6, int s7, int& x0, int& x1, int& x2,
+                        int& x3, int& t0, int& t1, int& t2, int& t3) {
+            int p1 = (s2 + s6) * c0541;
+            int a2 = p1 + s6 * c1847, a3 = p1 + s2 * c0765;
+            int a0 = (s0 + s4) * 4096, a1 = (s0 - s4) * 4096;
+            x0 = a0 + a3; x3 = a0 - a3; x1 = a1 + a2; x2 = a1 - a2;
+            t0 = s7; t1 = s5; t2 = s3; t3 = s1;
+            int p3 = t0 + t2, p4 = t1 + t3;
+            p1 = t0 + t3;
+            int p2 = t1 + t2;
+            const int p5 = (p3 + p4) * c1175;
+            t0 *= c0298; t1 *= c2053; t2 *= c3072; t3 *= c1501;
+            p1 = p5 + p1 * c0899; p2 = p5 + p2 * c2562; p3 *= c1961; p4 *= c0390;
+            t3 += p1 + p4; t2 += p2 + p3; t1 += p2 + p4; t0 += p1 + p3;
+        };
+        int val[64];
+        for (int i = 0; i < 8; i++) {
+            const short* dd = data + i;
+            int* v = val + i;
+            if (dd[8] == 0 && dd[16] == 0 && dd[24] == 0 && dd[32] == 0 && dd[40] == 0 && dd[48] == 0 && dd[56] == 0) {
+                const int dc = dd[0] * 4;
+                v[0] = v[8] = v[16] = v[24] = v[32] = v[40] = v[48] = v[56] = dc;
+            } else {
+                int x0, x1, x2, x3, t0, t1, t2, t3;
+                pass(dd[0], dd[8], dd[16], dd[24], dd[32], dd[40], dd[48], dd[56], x0, x1, x2, x3, t0, t1, t2, t3);
+                x0 += 512; x1 += 512; x2 += 512; x3 += 512;
+                v[0] = (x0 + t3) >> 10; v[56] = (x0 - t3) >> 10;
+                v[8] = (x1 + t2) >> 10; v[48] = (x1 - t2) >> 10;
+                v[16] = (x2 + t1) >> 10; v[40] = (x2 - t1) >> 10;
+                v[24] = (x3 + t0) >> 10; v[32] = (x3 - t0) >> 10;
+            }
+        }
+        for (int i = 0; i < 8; i++) {
+            const int* v = val + 8 * i;
+            uint8_t* o = out + (size_t)i * stride;
+            int x0, x1, x2, x3, t0, t1, t2, t3;
+            pass(v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7], x0, x1, x2, x3, t0, t1, t2, t3);
+            const int bias = 65536 + (128 << 17);
+            x0 += bias; x1 += bias; x2 += bias; x3 += bias;
+            o[0] = clamp8((x0 + t3) >> 17); o[7] = clamp8((x0 - t3) >> 17);
+            o[1] = clamp8((x1 + t2) >> 17); o[6] = clamp8((x1 - t2) >> 17);
+            o[2] = clamp8((x2 + t1) >> 17); o[5] = clamp8((x2 - t1) >> 17);
+            o[3] = clamp8((x3 + t0) >> 17); o[4] = clamp8((x3 - t0) >> 17);
+        }
+    }
+
+    bool decode(Image& out) {
+        static const uint8_t zigzag[64] = {0,  1,  8,  16, 9,  2,  3,  10, 17, 24, 32, 25, 18, 11, 4,  5,  12, 19, 26, 33, 40, 48,
+                                           41, 34, 27, 20, 13, 6,  7,  14, 21, 28, 35, 42, 49, 56, 57, 50, 43, 36, 29, 22, 15, 23,
+                                           30, 37, 44, 51, 58, 59, 52, 45, 38, 31, 39, 46, 53, 60, 61, 54, 47, 55, 62, 63};
+        if (n < 4 || d[0] != 0xff || d[1] != 0xd8) return fail("not a JPEG file");
+        pos = 2;
+        bool sawSof = false;
+        for (;;) {
+            int m = u8();
+            while (m != 0xff && pos < n) m = u8();
+            while (m == 0xff && pos < n) m = u8();
+            if (pos >= n) return fail("JPEG ended before the scan");
+            if (m == 0xd8 || (m >= 0xd0 && m <= 0xd7) || m == 0x01) continue;
+            const int len = u16();
+            if (len < 2 || pos + (size_t)len - 2 > n) return fail("bad JPEG segment");
+            const size_t end = pos + (size_t)len - 2;
+            if (m == 0xdb) {  // DQT
+                while (pos < end) {
+                    const int pq = u8();
+                    const int t = pq & 15, wide = pq >> 4;
+                    if (t > 3) return fail("bad DQT");
+                    for (int i = 0; i < 64; i++) qt[t][zigzag[i]] = (uint16_t)(wide ? u16() : u8());
+                }
+            } else if (m == 0xc4) {  // DHT
+                while (pos < end) {
+                    const int tc = u8();
+                    const int cls = tc >> 4, id = tc & 15;
+                    if (cls > 1 || id > 3) return fail("bad DHT");
+                    uint8_t counts[16];
+                    int total = 0;
+                    for (int i = 0; i < 16; i++) { counts[i] = (uint8_t)u8(); total += counts[i]; }
+                    if (total > 256) return fail("bad DHT");
+                    Huff& h = huff[cls][id];
+                    if (!buildHuff(h, counts)) return false;
+                    for (int i = 0; i < total; i++) h.val[i] = (uint8_t)u8();
+                }
+            } else if (m == 0xc0 || m == 0xc1) {  // SOF0 / SOF1 (extended sequential, Huffman)
+                if (u8() != 8) return fail("only 8-bit JPEG");
+                H = u16(); W = u16(); ncomp = u8();
+                if (W <= 0 || H <= 0 || (ncomp != 1 && ncomp != 3)) return fail("unsupported JPEG layout");
+                for (int i = 0; i < ncomp; i++) {
+                    comp[i].id = u8();
+                    const int hv = u8();
+                    comp[i].h = hv >> 4; comp[i].v = hv & 15;
+                    comp[i].tq = u8();
+                    if (comp[i].tq > 3) return fail("bad SOF");
+                }
+                for (int i = 0; i < ncomp; i++)
+                    if (comp[i].h != comp[0].h || comp[i].v != comp[0].v) return fail("chroma-subsampled JPEG not supported");
+                sawSof = true;
+            } else if (m == 0xc2) {
+                return fail("progressive JPEG not supported");
+            } else if (m == 0xdd) {
+                restart = u16();
+            } else if (m == 0xda) {  // SOS
+                if (!sawSof) return fail("SOS before SOF");
+                const int ns = u8();
+                if (ns != ncomp) return fail("non-interleaved JPEG scan not supported");
+                for (int i = 0; i < ns; i++) {
+                    const int id = u8(), t = u8();
+                    int k = 0;
+                    while (k < ncomp && comp[k].id != id) k++;
+                    if (k == ncomp) return fail("bad SOS");
+                    comp[k].td = t >> 4; comp[k].ta = t & 15;
+                    if (comp[k].td > 3 || comp[k].ta > 3 || !huff[0][comp[k].td].present || !huff[1][comp[k].ta].present)
+                        return fail("missing Huffman table");
+                }
+                pos = end;
+                break;
+            }
+            pos = end;
+        }
+        // ---- entropy-coded segment: one 8x8 block per component per MCU
+        const int bw = (W + 7) / 8, bh = (H + 7) / 8;
+        std::vector<uint8_t> plane[3];
+        const int pw = bw * 8;
+        for (int c = 0; c < ncomp; c++) plane[c].assign((size_t)pw * bh * 8, 0);
+        int todo = restart ? restart : 0x7fffffff;
+        for (int by = 0; by < bh; by++)
+            for (int bx = 0; bx < bw; bx++) {
+                for (int c = 0; c < ncomp; c++) {
+                    short blk[64];
+                    memset(blk, 0, sizeof blk);
+                    const int t = decodeSym(huff[0][comp[c].td]);
+                    if (t < 0 || t > 15) return fail("bad JPEG DC code");
+                    const int diff = t ? receiveExtend(t) : 0;
+                    comp[c].pred += diff;
+                    blk[0] = (short)(comp[c].pred * qt[comp[c].tq][0]);
+                    for (int k = 1; k < 64;) {
+                        const int rs = decodeSym(huff[1][comp[c].ta]);
+                        if (rs < 0) return fail("bad JPEG AC code");
+                        const int r = rs >> 4, sz = rs & 15;
+                        if (sz == 0) {
+                            if (rs != 0xf0) break;  // EOB
+                            k += 16;
+                        } else {
+                            k += r;
+                            if (k > 63) return fail("bad JPEG run");
+                            const int z = zigzag[k++];
+                            blk[z] = (short)(receiveExtend(sz) * qt[comp[c].tq][z]);
+                        }
+                    }
+                    idct(&plane[c][(size_t)by * 8 * pw + (size_t)bx * 8], pw, blk);
+                }
+                if (--todo <= 0) {  // restart interval: byte-align, expect RSTn, reset predictors
+                    if (bitcnt < 24) fill();
+                    if (!(hitMarker && marker >= 0xd0 && marker <= 0xd7)) {
+                        if (!(by == bh - 1 && bx == bw - 1)) return fail("missing JPEG restart marker");
+                    }
+                    bitbuf = 0; bitcnt = 0; hitMarker = false;
+                    for (int c = 0; c < ncomp; c++) comp[c].pred = 0;
+                    todo = restart;
+                }
+            }
+        // ---- output: grey, or YCbCr -> RGB in 20-bit fixed point
+        out.w = W; out.h = H; out.ch = ncomp;
+        out.px.resize((size_t)W * H * ncomp);
+        const bool isRGB = ncomp == 3 && comp[0].id == 'R' && comp[1].id == 'G' && comp[2].id == 'B';
+        auto f2fix = [](float x) { return ((int)(x * 4096.0f + 0.5f)) << 8; };
+        const int kCrR = f2fix(1.40200f), kCrG = -f2fix(0.71414f), kCbG = -f2fix(0.34414f), kCbB = f2fix(1.77200f);
+        for (int y = 0; y < H; y++)
+            for (int x = 0; x < W; x++) {
+                uint8_t* o = &out.px[((size_t)y * W + x) * ncomp];
+                const size_t i = (size_t)y * pw + x;
+                if (ncomp == 1) {
+                    o[0] = plane[0][i];
+                } else if (isRGB) {
+                    o[0] = plane[0][i]; o[1] = plane[1][i]; o[2] = plane[2][i];
+                } else {
+                    const int yf = (plane[0][i] << 20) + (1 << 19);
+                    const int cr = plane[2][i] - 128, cb = plane[1][i] - 128;
+                    const int r = yf + cr * kCrR;
+                    const int g = yf + cr * kCrG + (int)(((unsigned)(cb * kCbG)) & 0xffff0000u);
+                    const int b = yf + cb * kCbB;
+                    o[0] = clamp8(r >> 20); o[1] = clamp8(g >> 20); o[2] = clamp8(b >> 20);
+                }
+            }
+        return true;
+    }
+};
+
 bool loadTexture(const fs::path& p, Image& img, std::string& err) {
     std::ifstream f(p, std::ios::binary);
     if (!f) { err = "cannot open " + p.string(); return false; }
     std::vector<uint8_t> bytes((std::istreambuf_iterator<char>(f)), std::istreambuf_iterator<char>());
     std::string ext = p.extension().string();
     std::transform(ext.begin(), ext.end(), ext.begin(), ::tolower);
-    if (ext != ".png") {
-        err = "texture " + p.filename().string() + ": only PNG is decoded by the host library (JPEG: load an RTSC file "
-              "written by oracle/_ref/ref_host, or decode in the caller and use rth_set_texture)";
+    if (ext == ".jpg" || ext == ".jpeg") {
+        JpegDecoder jd(bytes.data(), bytes.size());
+        if (!jd.decode(img)) { err = p.filename().string() + ": " + jd.err; return false; }
+    } else if (ext == ".png") {
+        if (!decodePng(bytes, img, err)) { err = p.filename().string() + ": " + err; return false; }
+    } else {
+        err = "texture " + p.filename().string() + ": only PNG and baseline JPEG are decoded by the host library";
         return false;
     }
-    if (!decodePng(bytes, img, err)) { err = p.filename().string() + ": " + err; return false; }
     // stbi_set_flip_vertically_on_load(true), external/OpenGL/textureClass.cpp:65
     const size_t row = (size_t)img.w * img.ch;
     for (int y = 0; y < img.h / 2; y++)
