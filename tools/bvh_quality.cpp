@@ -69,6 +69,17 @@ static Bvh buildPLOC(int radius) { Bvh b; mortonSorted(b.order); int n = (int)tr
     cl.swap(next); iters++; }
   b.root = cl[0]; fprintf(stderr, "PLOC r=%d iterations %d\n", radius, iters); return b; }
 
+// Kensler-style tree rotations: for every inner node try swapping a child with a grandchild on the other side;
+// keep the swap that lowers the summed surface area most.  `passes` bottom-up sweeps.
+static void rotate(Bvh& b, int passes) {
+  std::vector<int> order; std::function<void(int)> post = [&](int n) { if (b.nodes[n].count) return; post(b.nodes[n].left); post(b.nodes[n].right); order.push_back(n); };
+  for (int p = 0; p < passes; p++) { order.clear(); post(b.root); int applied = 0;
+    for (int n : order) { Node& N = b.nodes[n]; int best = -1; float gain = 0;
+      for (int side = 0; side < 2; side++) { int c = side ? N.right : N.left, o = side ? N.left : N.right; if (b.nodes[o].count) continue; // swap c with a child of o
+        for (int k = 0; k < 2; k++) { int g = k ? b.nodes[o].right : b.nodes[o].left, keep = k ? b.nodes[o].left : b.nodes[o].right; Box nb = b.nodes[keep].box; nb.grow(b.nodes[c].box); float ga = b.nodes[o].box.area() - nb.area(); if (ga > gain) { gain = ga; best = side * 2 + k; } (void)g; } }
+      if (best >= 0) { int side = best >> 1, k = best & 1; int& c = side ? N.right : N.left; int o = side ? N.left : N.right; int& g = k ? b.nodes[o].right : b.nodes[o].left; std::swap(c, g); int keep = k ? b.nodes[o].left : b.nodes[o].right; Box nb = b.nodes[keep].box; nb.grow(b.nodes[g].box); b.nodes[o].box = nb; applied++; } }
+    fprintf(stderr, "rotation pass %d applied %d\n", p, applied); } }
+
 static double sahCost(const Bvh& b) { double c = 0; double ra = b.nodes[b.root].box.area(); for (auto& n : b.nodes) c += n.box.area() / ra * (n.count ? 1.0 : 1.2); return c; }
 static int depthOf(const Bvh& b, int n) { return b.nodes[n].count ? 1 : 1 + std::max(depthOf(b, b.nodes[n].left), depthOf(b, b.nodes[n].right)); }
 
@@ -94,5 +105,5 @@ int main(int argc, char** argv) { if (argc < 2) return 2; FILE* f = fopen(argv[1
     int ti; float t = trace(ref, o, d, dummy, ti); if (ti < 0) continue; V p = o + d * (t * 1.001f); const Tri& T = tris[ti]; V N = cross(T.b - T.a, T.c - T.a); N = N * (1 / std::sqrt(dot(N, N)));
     V r; do { r = {U(rng) * 2 - 1, U(rng) * 2 - 1, U(rng) * 2 - 1}; } while (dot(r, r) >= 1); r = r * (1 / std::sqrt(dot(r, r))); V nd = N + r; float nl = std::sqrt(dot(nd, nd)); if (nl < 1e-4f) continue; ro.push_back(p); rd.push_back(nd * (1 / nl)); }
   auto eval = [&](const char* name, const Bvh& b) { Stats st; int ti; for (size_t i = 0; i < ro.size(); i++) trace(b, ro[i], rd[i], st, ti); printf("%-12s nodes %8zu depth %3d SAH %8.2f  node visits/ray %7.2f  tri tests/ray %6.2f\n", name, b.nodes.size(), depthOf(b, b.root), sahCost(b), st.nodes / ro.size(), st.tris / ro.size()); fflush(stdout); };
-  eval("binned SAH", ref); { Bvh l = buildLBVH(); eval("LBVH", l); } for (int r : {10, 25}) { char nm[32]; snprintf(nm, 32, "PLOC r=%d", r); Bvh p = buildPLOC(r); eval(nm, p); }
+  eval("binned SAH", ref); { Bvh l = buildLBVH(); eval("LBVH", l); } for (int r : {10, 25}) { char nm[32]; snprintf(nm, 32, "PLOC r=%d", r); Bvh p = buildPLOC(r); eval(nm, p); if (r == 10) { for (int k = 0; k < 3; k++) { rotate(p, 2); snprintf(nm, 32, "PLOC+rot%d", 2 * (k + 1)); eval(nm, p); } } }
   return 0; }
