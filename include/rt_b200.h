@@ -110,7 +110,7 @@ typedef struct rt_uniforms {
 } rt_uniforms;
 
 /* Node, BVH.h:54-65 == compute.glsl:58-73.  48 bytes.  NOT consumed by the backend (the GPU builds
- * its own LBVH); declared here because the oracle and the reference harness exchange it. */
+ * its own BVH); declared here because the oracle and the reference harness exchange it. */
 typedef struct rt_ref_node {
     float bmin[3];
     float pad0;
@@ -164,9 +164,9 @@ typedef struct rt_counters {
     double extend_ms;       /* device time inside k_extend (CUDA events on the ctx stream)       */
     double shade_ms;        /* device time inside raygen/shade/accumulate/resolve                */
     double build_ms;        /* device time of the last rt_scene_build                            */
-    uint64_t bvh_nodes;     /* inner nodes of the LBVH                                           */
+    uint64_t bvh_nodes;     /* inner nodes of the GPU BVH                                        */
     uint64_t bvh_bytes;     /* bytes of node + triangle arrays traversal reads                   */
-    uint64_t bvh_depth;     /* longest leaf-to-root path of the LBVH                             */
+    uint64_t bvh_depth;     /* longest leaf-to-root path of the GPU BVH                          */
 } rt_counters;
 
 /* Host view of the GPU-built BVH, for validation only (tests check that every triangle lies in
@@ -210,8 +210,9 @@ int rt_scene_set_texture(rt_ctx* ctx, int32_t slot, const uint8_t* pixels, int32
                          int32_t height, int32_t channels);
 
 /* Replaces `BVH BVH(bvhTriangles, rtxTriangles)` (rayTracing.cpp:1293; BVH.h:150-220) and the node
- * SSBO upload (rayTracing.cpp:1324): builds an LBVH on the GPU (Morton codes, radix sort, Karras
- * hierarchy, bottom-up refit) and re-lays the triangles out for traversal. */
+ * SSBO upload (rayTracing.cpp:1324): builds a BVH on the GPU (Morton codes, radix sort, PLOC
+ * clustering — or the Karras LBVH with RT_BVH_BUILDER=lbvh — then 32-byte quantised nodes) and re-lays the
+ * triangles out for traversal. */
 int rt_scene_build(rt_ctx* ctx);
 
 /* ---------------------------------------------------------------- render

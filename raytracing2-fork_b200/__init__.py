@@ -4,7 +4,7 @@ This package is a thin ctypes view of two in-tree native libraries (built by ``m
 directory or by ``__graft_entry__.build()``):
 
 * ``librt_b200.so`` — the CUDA backend behind the C-ABI of ``include/rt_b200.h`` (hand-written
-  sm_100a kernels: LBVH build, wavefront raygen / extend / shade, resolve, finalize).  There is no CPU
+  sm_100a kernels: BVH build, wavefront raygen / extend / shade, resolve, finalize).  There is no CPU
   fallback: :class:`Backend` raises if the library or a CUDA device is missing.
 * ``librt_host.so`` — host-side scene assembly with the reference's surface (containers, camera,
   fixed materials, synthetic meshes, PNG out; ``host/rt_host.h``).

@@ -1,4 +1,4 @@
-// bvh_build.cu — LBVH construction on the GPU (replaces the reference's CPU builder,
+// bvh_build.cu — BVH construction on the GPU (replaces the reference's CPU builder,
 // RayTracing/Assets/headers/BVH.h:145-221, called at RayTracing/src/rayTracing.cpp:1293).
 //
 // Pipeline (all on the ctx stream, no host round trips apart from one 4-byte depth read-back):

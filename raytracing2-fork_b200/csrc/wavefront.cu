@@ -255,7 +255,7 @@ struct RayRegs {
 // Traversal stack: the first kShStack entries of every lane live in shared memory laid out
 // [level][thread], so a warp-wide push or pop is conflict-free (one bank pair per lane) whatever
 // the lanes' depths are; in local memory the same access scatters over up to 32 lines and costs up
-// to 32 L1TEX wavefronts.  Deeper entries (rare: LBVH depth is ~2 log2 n) overflow to local memory.
+// to 32 L1TEX wavefronts.  Deeper entries (rare: most rays keep fewer than 16 pending nodes) overflow to local memory.
 constexpr int kShStack = 16;
 struct Stack {
     int2* sh;         // &shared[0][threadIdx.x]; stride kExtBlock
