@@ -351,10 +351,20 @@ def run_gpu(args, rt):
             traffic = json.load(open(os.path.join(REPO, "profiles", "extend_traffic.json")))["dram_bytes_per_launch"]
         except Exception:
             pass
+        # SURVEY 8d's second term: flops(r) = n_inner*48 + n_tri*56 against the non-FMA FP32 issue peak
+        # (SMs x 128 lanes x SM clock; parity forbids FMA contraction, so one flop per lane per cycle)
+        props = torch.cuda.get_device_properties(local_rank)
+        sm_mhz = (clocks or {}).get("sm_mhz") or (clocks or {}).get("sm_max_mhz") or 1965.0
+        fp32_peak = props.multi_processor_count * 128 * sm_mhz * 1e6 * 1e-12
+        flops_per_seg = n_inner * 48 + n_tri * 56
+        fp32_achieved = flops_per_seg * seg_per_launch / avg_launch_s * 1e-12 if avg_launch_s > 0 else None
         roof = {"bound": "hbm", "kernel": "k_extend", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": (achieved / peak) if achieved else None, "traffic": traffic, "peak_source": peak_src,
                 "node_visits_per_segment": n_inner, "tri_tests_per_segment": n_tri,
                 "bytes_per_segment": bytes_per_seg, "segments_per_launch": seg_per_launch,
+                "fp32": {"achieved": fp32_achieved, "peak": fp32_peak, "unit": "TFLOP/s (non-FMA)",
+                         "frac": (fp32_achieved / fp32_peak) if fp32_achieved else None,
+                         "flops_per_segment": flops_per_seg},
                 "avg_launch_ms": avg_launch_s * 1e3, "extend_share_of_step": extend_ms / ms_total if ms_total else None,
                 "note": "algorithmic bytes = n_inner*64 + n_tri*48 + 96 per segment (SURVEY 8d); the 11 MB BVH of this "
                         "workload is L2-resident, so achieved can exceed the HBM peak — the bound that applies is "

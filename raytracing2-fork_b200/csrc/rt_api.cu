@@ -291,13 +291,10 @@ int prepare_image(rt_ctx* ctx, int W, int H) {
         ctx->rows.resize((size_t)H);
         for (int y = 0; y < H; y++) ctx->rows[(size_t)y] = y;
     }
-    const size_t P = (size_t)W * ctx->rows.size();
     CK(ctx->d_rows.reserve(std::max<size_t>(ctx->rows.size(), 1) * sizeof(int32_t)));
     if (!ctx->rows.empty())
         CK(cudaMemcpyAsync(ctx->d_rows.p, ctx->rows.data(), ctx->rows.size() * sizeof(int32_t), cudaMemcpyHostToDevice,
                            ctx->stream));
-    CK(ctx->d_accum.reserve(std::max<size_t>(P, 1) * sizeof(float4)));
-    CK(ctx->d_pixrng.reserve(std::max<size_t>(P, 1) * sizeof(uint32_t)));
     CK(ctx->d_image.reserve((size_t)W * H * sizeof(float4)));
     CK(ctx->d_sum.reserve((size_t)W * H * 3 * sizeof(uint32_t)));
     CK(ctx->d_out.reserve((size_t)W * H * 3));
@@ -306,20 +303,32 @@ int prepare_image(rt_ctx* ctx, int W, int H) {
     return RT_OK;
 }
 
-int lanes_for(rt_ctx* ctx, size_t P, int spp) {
-    if (ctx->cfg.rng_mode == RT_RNG_REF_PCG) return 1;  // the reference stream is sequential per pixel
+uint64_t path_budget(rt_ctx* ctx) {
     uint64_t budget = ctx->cfg.max_paths_in_flight ? ctx->cfg.max_paths_in_flight : ctx->default_budget;
-    uint64_t lanes = P ? budget / P : 1;
-    if (lanes < 1) lanes = 1;
-    if (lanes > (uint64_t)spp) lanes = (uint64_t)spp;
-    return (int)lanes;
+    return std::min<uint64_t>(std::max<uint64_t>(budget, 1), (uint64_t)1 << 30);  // slot ids are int32
 }
 
-int prepare_paths(rt_ctx* ctx, size_t slots) {
+// Shape of the wavefront batches for `count` frames of `spp` samples over P local pixels:
+// samples of one frame in flight together, and how many frames share a batch.
+void batch_shape(rt_ctx* ctx, size_t P, int spp, int count, int* samples, int* frames) {
+    const uint64_t budget = path_budget(ctx);
+    const uint64_t perPixel = std::max<uint64_t>(budget / std::max<size_t>(P, 1), 1);  // lanes of a pixel that fit
+    // the reference stream is sequential per pixel (compute.glsl:668,683): one sample of a frame at a time
+    const uint64_t s = ctx->cfg.rng_mode == RT_RNG_REF_PCG ? 1 : std::min<uint64_t>(perPixel, (uint64_t)spp);
+    uint64_t f = 1;
+    if (s == (uint64_t)spp || ctx->cfg.rng_mode == RT_RNG_REF_PCG) f = std::max<uint64_t>(perPixel / s, 1);
+    *samples = (int)s;
+    *frames = (int)std::min<uint64_t>(f, (uint64_t)std::max(count, 1));
+}
+
+int prepare_paths(rt_ctx* ctx, size_t slots, size_t frame_pixels) {
     slots = std::max<size_t>(slots, 1);
+    frame_pixels = std::max<size_t>(frame_pixels, 1);
     for (int i = 0; i < 6; i++) CK(ctx->d_path[i].reserve(slots * sizeof(float4)));
     CK(ctx->d_hit.reserve(slots * sizeof(float4)));
     CK(ctx->d_contrib.reserve(slots * sizeof(float4)));
+    CK(ctx->d_accum.reserve(frame_pixels * sizeof(float4)));
+    CK(ctx->d_pixrng.reserve(frame_pixels * sizeof(uint32_t)));
     return RT_OK;
 }
 
@@ -347,40 +356,60 @@ FrameParams make_params(rt_ctx* ctx, const rt_uniforms& u) {
     fp.height = (int)u.height;
     fp.local_pixels = (int)((size_t)u.width * ctx->rows.size());
     fp.rows = ctx->d_rows.as<int32_t>();
-    fp.lanes = 1;
     fp.lanes_active = 1;
+    fp.frames_in_batch = 1;
+    fp.samples_in_batch = 1;
+    fp.frame_stride = 1;
     return fp;
 }
 
-// one frame = numRaysPerPixel samples per local pixel, left in `accum`, resolved into image (+sum)
-int render_one_frame(rt_ctx* ctx, const rt_uniforms& u, bool add_to_sum) {
+// `count` frames with frameIndex = first, first + stride, …, each numRaysPerPixel samples per local pixel,
+// resolved into the image (+ the 8-bit sums).  Frames are batched together when they fit the path budget.
+int render_frames(rt_ctx* ctx, const rt_uniforms& u, uint32_t first, int stride, int count, bool add_to_sum) {
     const int W = (int)u.width, H = (int)u.height;
     int rc = prepare_image(ctx, W, H);
     if (rc) return rc;
     Launcher L = make_launcher(ctx);
     SceneView sc = make_view(ctx);
     FrameParams fp = make_params(ctx, u);
-    if (fp.local_pixels == 0) return RT_OK;
+    if (fp.local_pixels == 0 || count <= 0) return RT_OK;
     if (u.basicShading != 0) {
         WaveBuffers wb = make_wave(ctx);
+        fp.u.frameIndex = first + (uint32_t)((count - 1) * stride);
         CK(wf_preview(L, sc, wb, fp));
         return RT_OK;
     }
     const int spp = u.numRaysPerPixel;
-    const int lanes = lanes_for(ctx, (size_t)fp.local_pixels, spp);
-    rc = prepare_paths(ctx, (size_t)fp.local_pixels * lanes);
+    const size_t P = (size_t)fp.local_pixels;
+    int samples = 1, framesPerBatch = 1;
+    batch_shape(ctx, P, spp, count, &samples, &framesPerBatch);
+    rc = prepare_paths(ctx, P * samples * framesPerBatch, P * framesPerBatch);
     if (rc) return rc;
     WaveBuffers wb = make_wave(ctx);
-    fp.lanes = lanes;
-    CK(wf_clear_accum(L, wb, fp.local_pixels));
-    if (ctx->cfg.rng_mode == RT_RNG_REF_PCG) CK(wf_seed_pixels(L, sc, wb, fp));
-    for (int base = 0; base < spp; base += lanes) {
-        fp.sample_base = base;
-        fp.lanes_active = std::min(lanes, spp - base);
-        CK(wf_render_batch(L, sc, wb, fp));
+    fp.frame_stride = stride;
+    for (int done = 0; done < count; done += framesPerBatch) {
+        fp.u.frameIndex = first + (uint32_t)(done * stride);  // rayTracing.cpp:187
+        fp.frames_in_batch = std::min(framesPerBatch, count - done);
+        CK(wf_clear_accum(L, wb, (long long)P * fp.frames_in_batch));
+        if (ctx->cfg.rng_mode == RT_RNG_REF_PCG) CK(wf_seed_pixels(L, sc, wb, fp));
+        for (int base = 0; base < spp; base += samples) {
+            fp.sample_base = base;
+            fp.samples_in_batch = std::min(samples, spp - base);
+            fp.lanes_active = fp.frames_in_batch * fp.samples_in_batch;
+            CK(wf_render_batch(L, sc, wb, fp));
+        }
+        CK(wf_resolve_frame(L, wb, fp, add_to_sum));
+        // keep the event pool from overflowing on long screenshots
+        if (ctx->cfg.kernel_timing && ctx->ev_used > kEventCap - 512) {
+            CK(cudaStreamSynchronize(ctx->stream));
+            harvest_events(ctx);
+        }
     }
-    CK(wf_resolve_frame(L, wb, fp, add_to_sum));
     return RT_OK;
+}
+
+int render_one_frame(rt_ctx* ctx, const rt_uniforms& u, bool add_to_sum) {
+    return render_frames(ctx, u, u.frameIndex, 1, 1, add_to_sum);
 }
 
 // partial sums of the frames (or rows) this rank owns, left in d_sum
@@ -393,19 +422,14 @@ int render_partial(rt_ctx* ctx, const rt_uniforms* uniforms, int frames) {
     if (rc) return rc;
     CK(cudaMemsetAsync(ctx->d_sum.p, 0, (size_t)W * H * 3 * sizeof(uint32_t), ctx->stream));
     const bool frameSplit = ctx->cfg.split_mode == RT_SPLIT_FRAMES && ctx->cfg.world_size > 1;
-    for (int f = 0; f < frames; f++) {
-        if (frameSplit && (f % ctx->cfg.world_size) != ctx->cfg.rank) continue;
-        rt_uniforms uf = *uniforms;
-        uf.frameIndex = (uint32_t)f;  // rayTracing.cpp:187
-        uf.basicShading = 0;          // rayTracing.cpp:146 (SCREENSHOT_BASIC_SHADING)
-        rc = render_one_frame(ctx, uf, true);
-        if (rc) return rc;
-        // keep the event pool from overflowing on long screenshots
-        if (ctx->cfg.kernel_timing && ctx->ev_used > kEventCap - 512) {
-            CK(cudaStreamSynchronize(ctx->stream));
-            harvest_events(ctx);
-        }
-    }
+    rt_uniforms uf = *uniforms;
+    uf.basicShading = 0;  // rayTracing.cpp:146 (SCREENSHOT_BASIC_SHADING)
+    // frame f carries frameIndex = f (rayTracing.cpp:187); under RT_SPLIT_FRAMES this rank owns f % world == rank
+    const int first = frameSplit ? ctx->cfg.rank : 0;
+    const int stride = frameSplit ? ctx->cfg.world_size : 1;
+    const int count = first < frames ? (frames - first + stride - 1) / stride : 0;
+    rc = render_frames(ctx, uf, (uint32_t)first, stride, count, true);
+    if (rc) return rc;
     ctx->last_frames = frames;
     return RT_OK;
 }

@@ -46,17 +46,24 @@ struct FrameParams {
     rt_uniforms u;
     int32_t width, height;
     int32_t local_pixels;       // pixels this rank renders
-    int32_t lanes;              // samples of a pixel in flight together (1 in RT_RNG_REF_PCG mode)
+    // One batch of the wavefront holds `lanes_active` lanes of every local pixel; lane L carries sample
+    // sample_base + L % samples_in_batch of batch frame L / samples_in_batch, whose frameIndex is
+    // u.frameIndex + (L / samples_in_batch) * frame_stride.  Several frames share a batch whenever a whole
+    // frame needs fewer path slots than the budget (small images, tile split, RT_RNG_REF_PCG where a pixel's
+    // samples are sequential), so the persistent kernels always see large wavefronts.
     int32_t sample_base;        // first sample index of this batch
-    int32_t lanes_active;       // lanes of this batch that hold a real sample
+    int32_t lanes_active;       // frames_in_batch * samples_in_batch
+    int32_t frames_in_batch;    // >= 1
+    int32_t samples_in_batch;   // samples of one pixel of one frame in flight together (1 in RT_RNG_REF_PCG mode)
+    int32_t frame_stride;       // frameIndex step between batch frames (world_size under RT_SPLIT_FRAMES)
     const int32_t* rows;        // local row -> absolute row (RT_SPLIT_TILES), NULL = identity
 };
 struct WaveBuffers {
     PathArrays cur, next;
     float4* hit;          // t, u, v, slot(bits) per path of `cur`
     float4* contrib;      // radiance of each (lane, pixel) slot of the batch
-    float4* accum;        // running sum per local pixel (xyz) 
-    uint32_t* pix_rng;    // RT_RNG_REF_PCG: the per-pixel stream state carried across samples
+    float4* accum;        // running sum per (batch frame, local pixel) (xyz)
+    uint32_t* pix_rng;    // RT_RNG_REF_PCG: the per-(batch frame, pixel) stream state carried across samples
     uint32_t* counts;     // counts[b] = live paths entering bounce b (maxBounce + 2 entries), followed by
                           // the same number of k_extend work cursors
     unsigned long long* stats;  // [0] segments [1] paths [2] node visits [3] tri tests
@@ -87,7 +94,7 @@ struct Launcher {
 };
 
 int wf_extend_blocks_per_sm(bool instrument);
-cudaError_t wf_clear_accum(const Launcher& L, const WaveBuffers& wb, int local_pixels);
+cudaError_t wf_clear_accum(const Launcher& L, const WaveBuffers& wb, long long entries);
 cudaError_t wf_seed_pixels(const Launcher& L, const SceneView& sc, const WaveBuffers& wb, const FrameParams& fp);
 cudaError_t wf_render_batch(const Launcher& L, const SceneView& sc, const WaveBuffers& wb, const FrameParams& fp);
 cudaError_t wf_resolve_frame(const Launcher& L, const WaveBuffers& wb, const FrameParams& fp, bool add_to_sum);

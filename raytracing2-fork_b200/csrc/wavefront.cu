@@ -181,11 +181,14 @@ __device__ __forceinline__ void local_pixel_xy(const FrameParams& fp, int p, int
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kBlock) k_seed_pixels(const __grid_constant__ FrameParams fp,
                                                         uint32_t* __restrict__ pix_rng) {
-    const int p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= fp.local_pixels) return;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= fp.local_pixels * fp.frames_in_batch) return;
+    const int k = i / fp.local_pixels;
+    const int p = i - k * fp.local_pixels;
     int tx, ty;
     local_pixel_xy(fp, p, tx, ty);
-    pix_rng[p] = (uint32_t)tx + (uint32_t)ty * fp.u.width + fp.u.frameIndex * 968824447u;
+    const uint32_t frame = fp.u.frameIndex + (uint32_t)(k * fp.frame_stride);
+    pix_rng[i] = (uint32_t)tx + (uint32_t)ty * fp.u.width + frame * 968824447u;  // S:668
 }
 
 __global__ void __launch_bounds__(kBlock) k_clear_accum(float4* __restrict__ accum, int n) {
@@ -211,8 +214,11 @@ __global__ void __launch_bounds__(kBlock) k_raygen(const __grid_constant__ Frame
     int tx, ty;
     local_pixel_xy(fp, p, tx, ty);
     const PixelSetup ps = pixel_setup(fp.u, tx, ty);
+    const int k = lane / fp.samples_in_batch;  // batch frame
+    const int s = lane - k * fp.samples_in_batch;
+    const uint32_t frame = fp.u.frameIndex + (uint32_t)(k * fp.frame_stride);
     Rng<MODE> rng;
-    rng.init(MODE == 0 ? pix_rng[p] : (uint32_t)(fp.sample_base + lane), ps.pixelId, fp.u.frameIndex, 0u);
+    rng.init(MODE == 0 ? pix_rng[(size_t)k * fp.local_pixels + p] : (uint32_t)(fp.sample_base + s), ps.pixelId, frame, 0u);
     rng.stream(0u);
     V3 o, d;
     sample_ray(fp.u, ps, rng, o, d);
@@ -562,11 +568,14 @@ __global__ void __launch_bounds__(kBlock, 4) k_shade(const __grid_constant__ Sce
             flags = __float_as_uint(c.w);
             bool insideGlass = (flags >> 16) & 1u;
             const int bounceCount = bounce + 1;  // S:483
-            const int pixLocal = slotId % fp.local_pixels;
+            const int slotLane = slotId / fp.local_pixels;
+            const int pixLocal = slotId - slotLane * fp.local_pixels;
+            const int batchFrame = fp.frames_in_batch > 1 ? slotLane / fp.samples_in_batch : 0;
             int tx, ty;
             local_pixel_xy(fp, pixLocal, tx, ty);
             Rng<MODE> rng;
-            rng.init(carry, (uint32_t)tx + (uint32_t)ty * fp.u.width, fp.u.frameIndex, 0u);
+            rng.init(carry, (uint32_t)tx + (uint32_t)ty * fp.u.width,
+                     fp.u.frameIndex + (uint32_t)(batchFrame * fp.frame_stride), 0u);
             rng.stream((uint32_t)bounceCount);
 
             const int32_t hslot = __float_as_int(h.w);
@@ -657,7 +666,8 @@ __global__ void __launch_bounds__(kBlock, 4) k_shade(const __grid_constant__ Sce
             carry = rng.carry();
             if (terminated) {
                 contrib[slotId] = make_float4(radiance.x, radiance.y, radiance.z, 0.0f);
-                if (MODE == 0) pix_rng[pixLocal] = carry;  // the pixel's stream continues with the next sample
+                // the pixel's stream continues with the next sample of the same frame
+                if (MODE == 0) pix_rng[(size_t)batchFrame * fp.local_pixels + pixLocal] = carry;
             } else {
                 alive = true;
                 flags = (uint32_t)bounceCount | ((insideGlass ? 1u : 0u) << 16);
@@ -684,18 +694,23 @@ __global__ void __launch_bounds__(kBlock, 4) k_shade(const __grid_constant__ Sce
 __global__ void __launch_bounds__(kBlock) k_accumulate(const __grid_constant__ FrameParams fp,
                                                        const float4* __restrict__ contrib,
                                                        float4* __restrict__ accum) {
-    const int p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= fp.local_pixels) return;
-    float4 acc = accum[p];
-    for (int lane = 0; lane < fp.lanes_active; lane++) {  // sample order (S:683-694)
-        const float4 c = contrib[(size_t)lane * fp.local_pixels + p];
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;  // (batch frame, local pixel)
+    if (i >= fp.local_pixels * fp.frames_in_batch) return;
+    const int k = i / fp.local_pixels;
+    const int p = i - k * fp.local_pixels;
+    float4 acc = accum[i];
+    const float4* c0 = contrib + (size_t)k * fp.samples_in_batch * fp.local_pixels + p;
+    for (int s = 0; s < fp.samples_in_batch; s++) {  // sample order (S:683-694)
+        const float4 c = c0[(size_t)s * fp.local_pixels];
         acc.x = acc.x + c.x;
         acc.y = acc.y + c.y;
         acc.z = acc.z + c.z;
     }
-    accum[p] = acc;
+    accum[i] = acc;
 }
 
+// One thread per local pixel walks the batch frames in order: the image keeps the last frame (what the
+// reference's image binding holds after the last dispatch), the 8-bit sums take every frame (R:217-229).
 __global__ void __launch_bounds__(kBlock) k_resolve(const __grid_constant__ FrameParams fp,
                                                     const float4* __restrict__ accum, float4* __restrict__ image,
                                                     uint32_t* __restrict__ frame_sum, int add_to_sum) {
@@ -703,16 +718,23 @@ __global__ void __launch_bounds__(kBlock) k_resolve(const __grid_constant__ Fram
     if (p >= fp.local_pixels) return;
     int tx, ty;
     local_pixel_xy(fp, p, tx, ty);
-    const float4 a = accum[p];
     const float nr = (float)fp.u.numRaysPerPixel;
-    V3 color = v3(a.x / nr, a.y / nr, a.z / nr);  // S:696
-    color = tonemap_srgb(color);                  // S:697
     const size_t pix = (size_t)ty * fp.width + tx;
+    uint32_t sr = 0, sg = 0, sb = 0;
+    V3 color = v3(0.0f, 0.0f, 0.0f);
+    for (int k = 0; k < fp.frames_in_batch; k++) {
+        const float4 a = accum[(size_t)k * fp.local_pixels + p];
+        color = v3(a.x / nr, a.y / nr, a.z / nr);  // S:696
+        color = tonemap_srgb(color);               // S:697
+        sr += quantize8(color.x);
+        sg += quantize8(color.y);
+        sb += quantize8(color.z);
+    }
     image[pix] = make_float4(color.x, color.y, color.z, 1.0f);  // S:700
     if (add_to_sum) {
-        frame_sum[pix * 3 + 0] += quantize8(color.x);
-        frame_sum[pix * 3 + 1] += quantize8(color.y);
-        frame_sum[pix * 3 + 2] += quantize8(color.z);
+        frame_sum[pix * 3 + 0] += sr;
+        frame_sum[pix * 3 + 1] += sg;
+        frame_sum[pix * 3 + 2] += sb;
     }
 }
 
@@ -912,14 +934,14 @@ int wf_extend_blocks_per_sm(bool instrument) {
     return e == cudaSuccess && nb > 0 ? nb : 4;
 }
 
-cudaError_t wf_clear_accum(const Launcher& L, const WaveBuffers& wb, int local_pixels) {
-    k_clear_accum<<<nblocks(local_pixels), kBlock, 0, L.st>>>(wb.accum, local_pixels);
+cudaError_t wf_clear_accum(const Launcher& L, const WaveBuffers& wb, long long entries) {
+    k_clear_accum<<<nblocks(entries), kBlock, 0, L.st>>>(wb.accum, (int)entries);
     (*L.kernel_launches)++;
     return cudaGetLastError();
 }
 
 cudaError_t wf_seed_pixels(const Launcher& L, const SceneView&, const WaveBuffers& wb, const FrameParams& fp) {
-    k_seed_pixels<<<nblocks(fp.local_pixels), kBlock, 0, L.st>>>(fp, wb.pix_rng);
+    k_seed_pixels<<<nblocks((long long)fp.local_pixels * fp.frames_in_batch), kBlock, 0, L.st>>>(fp, wb.pix_rng);
     (*L.kernel_launches)++;
     return cudaGetLastError();
 }
@@ -971,7 +993,7 @@ cudaError_t wf_render_batch(const Launcher& L, const SceneView& sc, const WaveBu
     }
     {
         Timed t(L, 1);
-        k_accumulate<<<nblocks(fp.local_pixels), kBlock, 0, L.st>>>(fp, wb.contrib, wb.accum);
+        k_accumulate<<<nblocks((long long)fp.local_pixels * fp.frames_in_batch), kBlock, 0, L.st>>>(fp, wb.contrib, wb.accum);
         (*L.kernel_launches)++;
     }
     return cudaGetLastError();

@@ -271,6 +271,32 @@ def test_screenshot_rgb8_identical(classic, rng_mode):
     assert np.array_equal(be.screenshot_fetch(), ref)
 
 
+@pytest.mark.parametrize("rng_mode", [rt.RNG_REF_PCG, rt.RNG_PHILOX])
+def test_screenshot_frame_batching_is_invisible(classic, rng_mode):
+    """How many frames (and samples of a frame) share one wavefront batch depends on the path budget; the
+    8-bit sums and the last frame left in the image must not: a budget below one frame (samples split into
+    several batches), exactly one frame, 2 frames per batch with a remainder batch, and everything at once."""
+    scene, orc = classic
+    W, H, spp, frames = 48, 32, 6, 5
+    cam = rt.make_camera(W, H, (0.0, 0.0, 15.5))
+    u = rt.screenshot_uniforms(scene, cam, spp=spp, max_bounce=6, env_light=False)
+    ref, sums = orc.screenshot(u, frames, rng_mode=rng_mode)
+    ul = u.copy(); ul["frameIndex"] = frames - 1
+    last = orc.render_frame(ul, rng_mode=rng_mode)
+    P = W * H
+    for budget in (P * 4, P * spp, P * spp * 2, P * 2, P * spp * 64):
+        be = backend(scene, rng_mode=rng_mode, max_paths_in_flight=budget)
+        part = be.screenshot_partial(u, frames)
+        assert np.array_equal(part, sums), f"budget {budget}"
+        assert_image_equal(be.read_frame(), last, f"image after screenshot, budget {budget}")
+        be.close()
+    # frame split with a stride: rank 1 of 2 owns frames 1 and 3
+    be = backend(scene, rng_mode=rng_mode, split_mode=rt.SPLIT_FRAMES, rank=1, world_size=2, max_paths_in_flight=P * spp * 2)
+    _, s13 = orc.screenshot(u, frames, rng_mode=rng_mode, frame_list=np.array([1, 3]))
+    assert np.array_equal(be.screenshot_partial(u, frames), s13)
+    be.close()
+
+
 @pytest.mark.parametrize("split", [rt.SPLIT_TILES, rt.SPLIT_FRAMES])
 def test_rank_partials_sum_to_single_gpu_result(classic, split):
     """Multi-GPU sharding emulated rank by rank on one GPU: the partial 8-bit sums of 3 ranks add up
