@@ -8,7 +8,7 @@
 // dumping their results as raw arrays so that tests can pin the oracle and the product's host code
 // to them.  Built by oracle/Makefile into oracle/_ref/ref_host (git-ignored).  GLFW / GL / dialog
 // symbols stay unresolved at link time (-Wl,--unresolved-symbols=ignore-all): nothing here calls
-// them.  The GLSL hot path itself cannot be run this way (no OpenGL in this image).
+// them.  The GLSL hot path has its own harness: ref_shader.cpp (the shader source through glsl2cpp.py + glm).
 #include <cmath>
 #include <cstdint>
 #include <cstdio>

@@ -8,14 +8,21 @@
  * (RayTracing/Assets/Shaders/compute.glsl) and of the host pieces either side of it
  * (BVH.h builder, camera.h uniform derivation, screenshot() accumulation in rayTracing.cpp).
  *
- * PARITY UNPINNED (hot path): the reference executes this path only as GLSL on an OpenGL driver;
- * it ships no tests, golden vectors or fixtures, and no GL exists in the build image, so there is
- * no reference output to pin the shader restatement to.  What IS pinned against the real
- * reference code (compiled from /root/reference by oracle/Makefile into oracle/_ref/ref_host):
- * the BVH builder, the camera uniforms, the scene containers and the integer part of the RNG.
- * For everything else this oracle DEFINES the arithmetic: IEEE-754 binary32, round to nearest
- * even, no FMA contraction, glm 0.9.9.7 operation order, left-to-right evaluation of the two
- * jitter draws on compute.glsl:688, and the elementary functions specified in DESIGN.md §4.
+ * PARITY — what pins this restatement:
+ *   (1) the reference's OWN shader source: oracle/glsl2cpp.py rewrites compute.glsl syntactically and
+ *       oracle/ref_shader.cpp compiles it against the reference's vendored glm (oracle/_ref/libref_shader.so);
+ *       on the cases of tests/scenes.py (path-traced frames with every material type, textures, defocus, sky,
+ *       both preview variants) this oracle's RGBA32F frames are BIT-IDENTICAL to it
+ *       (tests/test_refshader_cpu.py; outputs committed as tests/golden/refshader_images.npz);
+ *   (2) the real reference host code compiled from /root/reference (oracle/_ref/ref_host): BVH builder,
+ *       camera uniforms, scene containers, loader, the integer part of the RNG.
+ * PARITY STILL UNPINNED: what only a GL driver supplies and the reference tree does not contain — the
+ * precision of cos / sin / exp / acos / pow, FMA contraction, the texture unit's filter arithmetic and the
+ * evaluation order of the two jitter draws on compute.glsl:688 (GLSL leaves it undefined).  No OpenGL exists
+ * in the build image and the reference ships no tests or golden vectors, so for those this oracle DEFINES the
+ * arithmetic: IEEE-754 binary32, round to nearest even, no contraction, left-to-right jitter draws, the
+ * elementary functions and the bilinear filter of DESIGN.md §4 (within 5 ulp of the same shader run with
+ * glibc's float functions).
  */
 #ifndef RT_ORACLE_H
 #define RT_ORACLE_H

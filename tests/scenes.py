@@ -1,0 +1,60 @@
+"""Scenes shared by the CPU and GPU parity tests and by tests/golden/make_golden_refshader.py."""
+import importlib
+
+import numpy as np
+
+rt = importlib.import_module("raytracing2-fork_b200")
+
+
+def material_zoo():
+    """CHECKER, GLASS, partial-smoothness SPECULAR, edge highlight, GLASS_HIGHLIGHT (magenta in trace), a light
+    slab and no container, so misses reach the procedural sky (compute.glsl:216-273, 521-546)."""
+    s = rt.Scene()
+    red = s.add_fixed_materials()
+    glass = s.add_glass((0.9, 0.95, 1.0), 1.5)
+    checker = s.add_checker(2.0)
+    metal = s.add_specular((0.8, 0.6, 0.2), (1, 1, 1), 0.7, 0.5)
+    m = np.zeros(1, dtype=rt.MATERIAL)
+    m["color"] = (0.2, 0.9, 0.3, 0); m["materialType"] = rt.MAT_DIFFUSE; m["isEdgeHighlight"] = 1; m["textureIndex"] = -1
+    edge = s.add_material(m)
+    m2 = np.zeros(1, dtype=rt.MATERIAL)
+    m2["color"] = (1, 1, 0, 0); m2["materialType"] = rt.MAT_GLASS_HIGHLIGHT; m2["textureIndex"] = -1
+    gh = s.add_material(m2)
+    s.add_cube((0, -1.5, 0), (12, 0.2, 12), (0, 0, 0), checker)
+    s.add_cube((-2.5, 0, 0), (1.5, 1.5, 1.5), (0.2, 0.5, 0.1), glass)
+    s.add_cube((0, 0, -1), (1.5, 1.5, 1.5), (0.0, 0.8, 0.3), metal)
+    s.add_cube((2.5, 0, 0), (1.5, 1.5, 1.5), (0.4, 0.1, 0.0), edge)
+    s.add_cube((0, 1.5, -3), (1, 1, 1), (0, 0, 0), gh)
+    s.add_cube((0, 3.5, 0), (2, 0.1, 2), (0, 0, 0), red + 3)
+    return s
+
+
+def zoo_camera(width=96, height=64):
+    return rt.make_camera(width, height, (0.0, 1.0, 12.0), pitch=0.05)
+
+
+# ---- the cases pinned against the reference's own shader source (tests/golden/refshader_*.npy)
+def refshader_cases():
+    """name -> (scene, uniforms).  RT_RNG_REF_PCG frames (the shader's own random stream) and previews."""
+    cases = {}
+    classic = rt.scene_classic_cornell()
+    cam = rt.make_camera(64, 64, (0.0, 0.0, 15.5))
+    cases["classic_64x64_spp16_d8"] = (classic, rt.screenshot_uniforms(classic, cam, spp=16, max_bounce=8, env_light=False))
+    camd = rt.make_camera(48, 48, (0.0, 0.0, 15.5), defocus=0.05)
+    u = rt.screenshot_uniforms(classic, camd, spp=6, max_bounce=5, env_light=False)
+    u["frameIndex"] = 3
+    cases["classic_defocus_48x48_frame3"] = (classic, u)
+    up = rt.interactive_uniforms(classic, cam)
+    cases["classic_preview_64x64"] = (classic, up)
+    ups = up.copy(); ups["basicShadingShadow"] = 1
+    cases["classic_preview_shadow_64x64"] = (classic, ups)
+    zoo = material_zoo()
+    cases["zoo_96x64_spp8_d10_env"] = (zoo, rt.screenshot_uniforms(zoo, zoo_camera(), spp=8, max_bounce=10, env_light=True))
+    cases["zoo_preview_96x64"] = (zoo, rt.interactive_uniforms(zoo, zoo_camera()))
+    sph = rt.scene_textured_sphere(n_quads=24, container="cornell", tex_size=64)
+    cams = rt.camera_for_box(sph, 80, 60)
+    cases["sphere_cornell_80x60_spp8_d8"] = (sph, rt.screenshot_uniforms(sph, cams, spp=8, max_bounce=8, env_light=False))
+    mir = rt.scene_textured_sphere(n_quads=16, container="mirror", tex_size=32)
+    camm = rt.camera_for_box(mir, 64, 48)
+    cases["sphere_mirror_64x48_spp4_d12"] = (mir, rt.screenshot_uniforms(mir, camm, spp=4, max_bounce=12, env_light=False))
+    return cases

@@ -4,11 +4,13 @@ must be bit-exact; binary32 results are also required to be bit-exact because or
 evaluate the same operation order without FMA contraction — the tolerance written in
 each test is therefore 0 ulp, with a PSNR floor reported alongside for the record."""
 import importlib
+import os
 
 import numpy as np
 import pytest
 
 import oracle
+import scenes
 
 rt = importlib.import_module("raytracing2-fork_b200")
 pytestmark = pytest.mark.gpu
@@ -212,28 +214,29 @@ def test_frame_with_small_path_budget_is_identical(classic):
         assert_image_equal(be.read_frame(), ref, f"budget {budget}")
 
 
+_REFSHADER_CASES = scenes.refshader_cases()
+
+
+@pytest.mark.parametrize("name", sorted(_REFSHADER_CASES))
+def test_frame_equals_reference_shader_golden(name):
+    """The CUDA path against the reference's OWN shader source, no oracle in between: tests/golden/
+    refshader_images.npz holds what compute.glsl computes for these cases when compiled as C++ against the
+    reference's glm over the reference's BVH (tests/golden/make_golden_refshader.py).  RT_RNG_REF_PCG reproduces
+    the shader's random stream, so every float of the RGBA32F image has to match."""
+    scene, u = _REFSHADER_CASES[name]
+    ref = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "refshader_images.npz"))[name]
+    be = backend(scene, rng_mode=rt.RNG_REF_PCG)
+    be.render_frame(u)
+    assert_image_equal(be.read_frame(), ref, f"reference shader golden {name}")
+    be.close()
+
+
 def test_all_material_types_and_env_light():
     """CHECKER, GLASS, partial-smoothness SPECULAR, edge highlight, GLASS_HIGHLIGHT (magenta in trace),
     and the procedural sky on a miss (compute.glsl:216-273, 521-546)."""
-    s = rt.Scene()
-    red = s.add_fixed_materials()
-    glass = s.add_glass((0.9, 0.95, 1.0), 1.5)
-    checker = s.add_checker(2.0)
-    metal = s.add_specular((0.8, 0.6, 0.2), (1, 1, 1), 0.7, 0.5)
-    m = np.zeros(1, dtype=rt.MATERIAL)
-    m["color"] = (0.2, 0.9, 0.3, 0); m["materialType"] = rt.MAT_DIFFUSE; m["isEdgeHighlight"] = 1; m["textureIndex"] = -1
-    edge = s.add_material(m)
-    m2 = np.zeros(1, dtype=rt.MATERIAL)
-    m2["color"] = (1, 1, 0, 0); m2["materialType"] = rt.MAT_GLASS_HIGHLIGHT; m2["textureIndex"] = -1
-    gh = s.add_material(m2)
-    s.add_cube((0, -1.5, 0), (12, 0.2, 12), (0, 0, 0), checker)
-    s.add_cube((-2.5, 0, 0), (1.5, 1.5, 1.5), (0.2, 0.5, 0.1), glass)
-    s.add_cube((0, 0, -1), (1.5, 1.5, 1.5), (0.0, 0.8, 0.3), metal)
-    s.add_cube((2.5, 0, 0), (1.5, 1.5, 1.5), (0.4, 0.1, 0.0), edge)
-    s.add_cube((0, 1.5, -3), (1, 1, 1), (0, 0, 0), gh)
-    s.add_cube((0, 3.5, 0), (2, 0.1, 2), (0, 0, 0), red + 3)
+    s = scenes.material_zoo()
     orc = oracle.OracleScene.from_scene(s)
-    cam = rt.make_camera(96, 64, (0.0, 1.0, 12.0), pitch=0.05)
+    cam = scenes.zoo_camera()
     for rng_mode in (rt.RNG_REF_PCG, rt.RNG_PHILOX):
         u = rt.screenshot_uniforms(s, cam, spp=8, max_bounce=10, env_light=True)
         be = backend(s, rng_mode=rng_mode)

@@ -1,0 +1,106 @@
+"""The oracle pinned against the reference's OWN shader source (CPU tests, no GPU).
+
+oracle/_ref/libref_shader.so is RayTracing/Assets/Shaders/compute.glsl itself — rewritten syntactically by
+oracle/glsl2cpp.py, compiled with g++ -ffp-contract=off against the reference's vendored glm 0.9.9.7, run over
+the node array the reference's own BVH.h builds (oracle/_ref/ref_host).  It exists wherever `make -C oracle`
+saw /root/reference (this container; the built library travels to the GPU box).  The committed
+tests/golden/refshader_images.npz are its outputs; the tests below hold
+
+  * golden == reference shader, regenerated here           (skipped without the library)
+  * oracle == golden, bit for bit, every case              (always)
+  * reference shader with libm's cosf/sinf/expf/acosf/powf instead of the spec'd elementary functions stays
+    within a few ulp of the golden                         (skipped without the library)
+"""
+import json
+import os
+import zlib
+
+import numpy as np
+import pytest
+
+import oracle
+import refshader
+import scenes
+
+rt = scenes.rt
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+CASES = scenes.refshader_cases()
+
+
+@pytest.fixture(scope="module")
+def golden():
+    z = np.load(os.path.join(GOLD, "refshader_images.npz"))
+    meta = json.load(open(os.path.join(GOLD, "refshader.json")))
+    assert sorted(z.files) == sorted(CASES) == sorted(meta)
+    for k in z.files:
+        assert (zlib.crc32(z[k].tobytes()) & 0xffffffff) == meta[k]["crc"]
+    return z
+
+
+def bits(a):
+    return np.ascontiguousarray(a, dtype=np.float32).view(np.uint32)
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_oracle_equals_reference_shader_golden(golden, name):
+    scene, u = CASES[name]
+    img = oracle.OracleScene.from_scene(scene).render_frame(u, rng_mode=rt.RNG_REF_PCG)
+    ref = golden[name]
+    assert img.shape == ref.shape
+    diff = bits(img) != bits(ref)
+    assert not diff.any(), f"{name}: {int(diff.sum())} of {diff.size} floats differ from the reference shader"
+
+
+@pytest.mark.skipif(not refshader.available(True), reason="oracle/_ref/libref_shader.so not built (needs /root/reference)")
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_golden_is_what_the_reference_shader_computes(golden, name):
+    scene, u = CASES[name]
+    assert np.array_equal(bits(refshader.render(scene, u, spec_math=True)), bits(golden[name]))
+
+
+@pytest.mark.skipif(not refshader.available(False), reason="oracle/_ref/libref_shader_libm.so not built")
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_libm_elementary_functions_stay_within_ulps(golden, name):
+    """cos / sin / exp / acos / pow are a GL driver's in the reference; with glibc's float versions in their place
+    the stored sRGB floats move by a few ulp at most (pow(x, 1/2.2) is the only one on every pixel)."""
+    scene, u = CASES[name]
+    img = refshader.render(scene, u, spec_math=False)
+    d = np.abs(bits(img).astype(np.int64) - bits(golden[name]).astype(np.int64))
+    assert d.max() <= 8, f"{name}: {d.max()} ulp"
+    q = lambda x: np.floor(np.clip(x[..., :3], 0, 1) * 255.0 + 0.5)
+    assert (q(img) != q(golden[name])).mean() < 1e-3   # the RGB8 blit agrees but for rounding-boundary cases
+
+
+def test_translator_is_syntactic():
+    """glsl2cpp.py on a probe: qualifiers dropped, float suffixes, references, swizzles, hoisted random() pair."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("glsl2cpp", os.path.join(os.path.dirname(GOLD), "..", "oracle", "glsl2cpp.py"))
+    g = importlib.util.module_from_spec(spec); spec.loader.exec_module(g)
+    src = """#version 430 core
+layout (local_size_x = 8) in;
+layout(binding = 1, std430) buffer B { Thing things[]; };
+layout(binding = 3, std140) uniform U { int n; vec4 p; };
+float f(inout uint s, out bool b) { return 2.0 * 1e-6 + 1.5f + p.xyz.x; }
+void main()
+{
+    vec3 e = a + b.xyz * random(-0.5f, 0.5f, s) + c.xyz * random(-0.5f, 0.5f, s);
+    switch (k)
+    {
+        case 0:
+            vec3 d = vec3(1.0);
+            break;
+    }
+    vec3 g = vec3(0.5);
+}
+"""
+    out = g.translate(src)
+    assert "#version" not in out and "layout" not in out and "uniform" not in out
+    assert "Thing* things;" in out and "int n;" in out
+    assert "float f(uint& s, bool& b)" in out
+    assert "2.0f * 1e-6f + 1.5f + xyz(p).x" in out
+    assert "void shader_main()" in out
+    assert "vec3 d; d = vec3(1.0f);" in out and "vec3 g = vec3(0.5f);" in out
+    lines = [l.strip() for l in out.split("\n")]
+    i = lines.index("float _rnd0 = random(-0.5f, 0.5f, s);")
+    assert lines[i + 1] == "float _rnd1 = random(-0.5f, 0.5f, s);"
+    assert lines[i + 2] == "vec3 e = a + xyz(b) * _rnd0 + xyz(c) * _rnd1;"
