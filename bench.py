@@ -132,9 +132,18 @@ def pinned_copy(torch, a: np.ndarray) -> np.ndarray:
 
 
 # ------------------------------------------------------------------------------------------------ CPU arm
-def cpu_sample(rt, threads=0):
-    """Oracle port on the host cores: a centred crop of the config-2 image at reduced spp (throughput in
-    Mrays/s does not depend on spp or crop size).  Returns (Mrays/s, seconds, segments, threads)."""
+_CPU_ARM = {}
+
+
+def cpu_arm(rt):
+    """The CPU implementation that gets timed, prepared once: the reference's OWN compute shader source
+    (oracle/_ref/libref_shader_libm.so: compute.glsl rewritten syntactically by oracle/glsl2cpp.py, compiled with
+    g++ -O2 against the reference's glm, libm elementary functions; built where /root/reference exists and shipped
+    prebuilt) over the reference's BVH — `kind: "reference"`.  If that library is missing the oracle port is
+    timed instead — `kind: "port"`.  Either way the segment count comes from the oracle on the identical frame
+    (RT_RNG_REF_PCG: the oracle's frame is bit-identical to the shader's, tests/test_refshader_cpu.py)."""
+    if _CPU_ARM:
+        return _CPU_ARM
     import oracle  # the CPU baseline leg is one of the two places allowed to execute oracle/
     scene, cam, u = build_workload(rt, WORKLOAD["width"], WORKLOAD["height"])
     orc = oracle.OracleScene.from_scene(scene)
@@ -143,20 +152,55 @@ def cpu_sample(rt, threads=0):
     W, H = WORKLOAD["width"], WORKLOAD["height"]
     x0, y0 = (W - CPU_SAMPLE["crop_w"]) // 2, (H - CPU_SAMPLE["crop_h"]) // 2
     region = (x0, y0, x0 + CPU_SAMPLE["crop_w"], y0 + CPU_SAMPLE["crop_h"])
+    _CPU_ARM.update(orc=orc, u=uu, region=region, shader=None, kind="port", segments=None)
+    try:
+        import refshader
+        if refshader.available(False):
+            tris, _ = orc.permuted()   # the oracle's BVH is pinned to the reference builder's (tests/test_oracle_cpu.py)
+            _CPU_ARM["shader"] = refshader.Loaded(scene, spec_math=False, bvh=(orc.nodes(), tris))
+            _CPU_ARM["kind"] = "reference"
+            cn = oracle.OrcCounters()
+            for f in range(CPU_SAMPLE["frames"]):
+                uu["frameIndex"] = f
+                orc.render_frame(uu, rng_mode=rt.RNG_REF_PCG, region=region, counters=cn)
+            _CPU_ARM["segments"] = int(cn.segments)
+    except Exception as e:  # a missing or stale harness must not take the bench down
+        print(f"bench.py: reference shader harness unavailable ({e}); timing the oracle port", file=sys.stderr)
+        _CPU_ARM.update(shader=None, kind="port", segments=None)
+    return _CPU_ARM
+
+
+def cpu_sample(rt, threads=0):
+    """One bounded CPU sample: a centred crop of the config-2 image at reduced spp (throughput in Mrays/s does not
+    depend on spp or crop size).  Returns (Mrays/s, seconds, segments, threads)."""
+    import oracle
+    arm = cpu_arm(rt)
+    uu, region = arm["u"], arm["region"]
+    nthreads = threads if threads > 0 else (os.cpu_count() or 1)
+    if arm["shader"] is not None:
+        t0 = time.perf_counter()
+        for f in range(CPU_SAMPLE["frames"]):
+            uu["frameIndex"] = f
+            arm["shader"].render(uu, region=region, threads=threads)
+        dt = time.perf_counter() - t0
+        return arm["segments"] / dt * 1e-6, dt, arm["segments"], nthreads
     cn = oracle.OrcCounters()
     t0 = time.perf_counter()
     for f in range(CPU_SAMPLE["frames"]):
         uu["frameIndex"] = f
-        orc.render_frame(uu, rng_mode=rt.RNG_PHILOX, threads=threads, region=region, counters=cn)
+        arm["orc"].render_frame(uu, rng_mode=rt.RNG_PHILOX, threads=threads, region=region, counters=cn)
     dt = time.perf_counter() - t0
-    nthreads = threads if threads > 0 else (os.cpu_count() or 1)
     return cn.segments / dt * 1e-6, dt, int(cn.segments), nthreads
 
 
-def sample_text():
-    return (f"centred {CPU_SAMPLE['crop_w']}x{CPU_SAMPLE['crop_h']} crop of the 1920x1080 config-2 image, "
-            f"{CPU_SAMPLE['frames']} frame x {CPU_SAMPLE['spp']} spp, depth {WORKLOAD['max_bounce']}, Philox, "
-            f"oracle port of compute.glsl with the reference's own BVH (BVH.h), std::thread over rows")
+def sample_text(rt=None):
+    base = (f"centred {CPU_SAMPLE['crop_w']}x{CPU_SAMPLE['crop_h']} crop of the 1920x1080 config-2 image, "
+            f"{CPU_SAMPLE['frames']} frame x {CPU_SAMPLE['spp']} spp, depth {WORKLOAD['max_bounce']}, ")
+    if _CPU_ARM.get("kind") == "reference":
+        return base + ("the reference's own compute.glsl compiled for the CPU (glsl2cpp.py + glm, g++ -O2, libm) over the "
+                       "reference's BVH (BVH.h), the shader's PCG stream, std::thread over rows; segments counted by the oracle "
+                       "on the identical frame")
+    return base + "Philox, oracle port of compute.glsl with the reference's own BVH (BVH.h), std::thread over rows"
 
 
 def run_reference(args, rt):
@@ -174,7 +218,8 @@ def run_reference(args, rt):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": float(np.mean(secs)) * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": workload_config(args.gpus),
-        "cpu_baseline": {"value": value, "unit": "Mrays/s", "cores": nthreads, "kind": "port", "sample": sample_text()},
+        "cpu_baseline": {"value": value, "unit": "Mrays/s", "cores": nthreads, "kind": _CPU_ARM.get("kind", "port"),
+                         "sample": sample_text()},
         "e2e": {"value": value, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -373,7 +418,15 @@ def run_gpu(args, rt):
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         v, dt, segs, nthreads = cpu_sample(rt)
-        cpu = {"value": v, "unit": "Mrays/s", "cores": nthreads, "kind": "port", "sample": sample_text(),
+        port = None
+        if _CPU_ARM.get("kind") == "reference":   # for the record: the oracle port on the same crop (Philox), same threads
+            import oracle
+            cn = oracle.OrcCounters()
+            t0 = time.perf_counter()
+            _CPU_ARM["orc"].render_frame(_CPU_ARM["u"], rng_mode=rt.RNG_PHILOX, region=_CPU_ARM["region"], counters=cn)
+            port = {"value": cn.segments / (time.perf_counter() - t0) * 1e-6, "unit": "Mrays/s", "kind": "port"}
+        cpu = {"value": v, "unit": "Mrays/s", "cores": nthreads, "kind": _CPU_ARM.get("kind", "port"), "sample": sample_text(),
+               "oracle_port": port,
                "seconds": dt, "segments": segs}
 
     if rank == 0:

@@ -1,9 +1,9 @@
 // ref_shader.cpp — runs the reference's OWN compute shader source on the CPU (TEST INFRASTRUCTURE ONLY).
 //
 // This file contains no reference code.  oracle/glsl2cpp.py rewrites
-// /root/reference/RayTracing/Assets/Shaders/compute.glsl into oracle/_ref/compute_glsl.inc (a purely
-// syntactic rewrite: qualifiers dropped, `inout` → references, `f` suffixes on float literals, `.xyz` →
-// `xyz()`), and this harness #includes that file inside a namespace whose vocabulary is the reference's
+// /root/reference/RayTracing/Assets/Shaders/compute.glsl into oracle/_ref/compute_glsl.inc, which exists only
+// while this file compiles (a syntactic rewrite: qualifiers dropped, `inout` → references, `f` suffixes on
+// float literals, `.xyz` → `xyz()`, see the script), and this harness #includes it inside a namespace whose vocabulary is the reference's
 // own vendored glm 0.9.9.7 (/root/reference/external/glm: vec2/3/4, dot, cross, normalize, reflect, mix,
 // clamp, smoothstep, mod, …).  So every statement executed for a pixel — RNG, ray generation, the BVH
 // walk over the reference's own node array, Möller–Trumbore, the material switch, Russian roulette,
@@ -18,7 +18,8 @@
 //                                                        REF_SPEC_MATH=0: glm → libm (cosf, expf, powf …)
 //   * vec3 / int, mod(float, int)                        GLSL's implicit int → float conversion
 // Built by oracle/Makefile into oracle/_ref/libref_shader.so (+ libref_shader_libm.so); it pins the
-// oracle (tests/test_refshader_cpu.py) and mints tests/golden/refshader_*.npy for the GPU parity tests.
+// oracle (tests/test_refshader_cpu.py), mints tests/golden/refshader_images.npz for the GPU parity tests and is
+// the CPU arm of bench.py (`cpu_baseline.kind = "reference"`).
 #include <cmath>
 #include <cstdint>
 #include <cstring>
@@ -192,8 +193,9 @@ int refsh_set_texture(int32_t slot, const uint8_t* px, int32_t w, int32_t h, int
     return 0;
 }
 
-// UBO.Update + glDispatchCompute(W/8, H/4, 1): one shader_main() per pixel into rgba32f (row 0 = bottom)
-int refsh_render(const rt_uniforms* u, float* rgba32f, int threads) {
+// UBO.Update + glDispatchCompute: one shader_main() per pixel of [x0,x1) x [y0,y1) into rgba32f (W*H*4 floats, row 0
+// = bottom; pixels outside the region are left untouched)
+int refsh_render_region(const rt_uniforms* u, float* rgba32f, int32_t x0, int32_t y0, int32_t x1, int32_t y1, int threads) {
     using namespace glsl;
     if (!u || !rgba32f || g_nodes.empty()) return 1;
     pad = u->pad; numTextures = u->numTextures; width = u->width; height = u->height;
@@ -210,20 +212,30 @@ int refsh_render(const rt_uniforms* u, float* rgba32f, int threads) {
     imgOutput.w = (int)u->width;
     imgOutput.h = (int)u->height;
     const int W = (int)u->width, H = (int)u->height;
+    if (x0 < 0) x0 = 0;
+    if (y0 < 0) y0 = 0;
+    if (x1 > W) x1 = W;
+    if (y1 > H) y1 = H;
+    if (x1 <= x0 || y1 <= y0) return 0;
     if (threads <= 0) threads = (int)std::thread::hardware_concurrency();
     if (threads < 1) threads = 1;
-    if (threads > H) threads = H;
+    if (threads > y1 - y0) threads = y1 - y0;
     std::vector<std::thread> pool;
     for (int t = 0; t < threads; t++)
         pool.emplace_back([=]() {
-            for (int y = t; y < H; y += threads)
-                for (int x = 0; x < W; x++) {
+            for (int y = y0 + t; y < y1; y += threads)
+                for (int x = x0; x < x1; x++) {
                     gl_GlobalInvocationID.xy = uvec2((unsigned)x, (unsigned)y);
                     shader_main();
                 }
         });
     for (auto& th : pool) th.join();
     return 0;
+}
+
+int refsh_render(const rt_uniforms* u, float* rgba32f, int threads) {
+    if (!u) return 1;
+    return refsh_render_region(u, rgba32f, 0, 0, (int32_t)u->width, (int32_t)u->height, threads);
 }
 
 int refsh_spec_math(void) { return REF_SPEC_MATH; }
