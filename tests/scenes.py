@@ -57,4 +57,31 @@ def refshader_cases():
     mir = rt.scene_textured_sphere(n_quads=16, container="mirror", tex_size=32)
     camm = rt.camera_for_box(mir, 64, 48)
     cases["sphere_mirror_64x48_spp4_d12"] = (mir, rt.screenshot_uniforms(mir, camm, spp=4, max_bounce=12, env_light=False))
+    # createDiverseCornellBox (rayTracing.cpp:1071-1118): glass, mirror, checker and metal cubes in the classic room
+    div = rt.Scene()
+    red = div.add_fixed_materials()
+    glass = div.add_glass((1.0, 1.0, 1.0), 1.5)
+    checker = div.add_checker(1.0)
+    metal = div.add_specular((0.9, 0.7, 0.3), (1, 1, 1), 0.85, 0.6)
+    div.create_diverse_cornell_box(10.0, red, red + 1, red + 2, red + 3, glass, red + 4, checker, metal)
+    cases["diverse_64x64_spp8_d12"] = (div, rt.screenshot_uniforms(div, cam, spp=8, max_bounce=12, env_light=False))
+    # addSkyLightPlane (rayTracing.cpp:388-432; duplicate triangles on purpose) over a sphere, sky on misses
+    sky = rt.Scene()
+    sky.set_procedural_texture(0, 32)
+    tex = sky.add_textured(0)
+    sky.add_displaced_sphere(12, (0.0, 0.0, 0.0), 3.0, 0.05, tex)
+    r2 = sky.add_fixed_materials()
+    sky.add_sky_light_plane(r2 + 3)
+    camk = rt.make_camera(72, 48, (0.0, 2.0, 14.0), pitch=0.1)
+    cases["sky_sphere_72x48_spp6_d6_env"] = (sky, rt.screenshot_uniforms(sky, camk, spp=6, max_bounce=6, env_light=True))
+    # addSideLitCornellBox (rayTracing.cpp:690-847), rotated variant
+    side = rt.Scene()
+    side.set_procedural_texture(0, 32)
+    t2 = side.add_textured(0)
+    side.add_displaced_sphere(10, (0.0, 0.0, 0.0), 3.0, 0.05, t2)
+    r3 = side.add_fixed_materials()
+    d = rt.defaults()
+    side.add_side_lit_cornell_box(d.cornell_light_size, d.cornell_padding, r3 + 3, r3 + 2, True)
+    camsd = rt.camera_for_box(side, 64, 48)
+    cases["sphere_sidelit_64x48_spp6_d8"] = (side, rt.screenshot_uniforms(side, camsd, spp=6, max_bounce=8, env_light=False))
     return cases
