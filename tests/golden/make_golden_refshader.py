@@ -9,7 +9,7 @@ functions (cos, sin, exp, acos, pow) are the spec'd ones of DESIGN.md §4 (REF_S
 The GPU parity tests compare the CUDA path against these files bit for bit, without the oracle in between;
 tests/test_refshader_cpu.py keeps the oracle pinned to them as well.
 
-    python tests/golden/make_golden_refshader.py
+    python tests/golden/make_golden_refshader.py [--big]
 """
 import json
 import os
@@ -36,6 +36,15 @@ def main():
                       "triangles": int(scene.triangles.size), "unique_values": int(np.unique(img).size)}
         print(name, meta[name])
     np.savez_compressed(os.path.join(HERE, "refshader_images.npz"), **images)
+    if "--big" in sys.argv:   # minutes of CPU: the full-size cases, CRC only
+        big = {}
+        for name, (scene, u) in scenes.refshader_big_cases().items():
+            img = refshader.render(scene, u, spec_math=True)
+            big[name] = {"crc": zlib.crc32(img.tobytes()) & 0xffffffff, "shape": list(img.shape),
+                         "triangles": int(scene.triangles.size),
+                         "row_crc": [zlib.crc32(img[y].tobytes()) & 0xffffffff for y in range(img.shape[0])]}
+            print(name, big[name]["crc"])
+        json.dump(big, open(os.path.join(HERE, "refshader_big.json"), "w"), indent=0, sort_keys=True)
     json.dump(meta, open(os.path.join(HERE, "refshader.json"), "w"), indent=1, sort_keys=True)
 
 

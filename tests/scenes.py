@@ -85,3 +85,17 @@ def refshader_cases():
     camsd = rt.camera_for_box(side, 64, 48)
     cases["sphere_sidelit_64x48_spp6_d8"] = (side, rt.screenshot_uniforms(side, camsd, spp=6, max_bounce=8, env_light=False))
     return cases
+
+
+def refshader_big_cases():
+    """Full-size cases pinned by CRC only (tests/golden/refshader.json → "crc_only"): BASELINE config 1 exactly
+    (512x512, one 64-spp frame, depth 8, classic Cornell box) and the config-2 scene (100 368 triangles, depth 20)
+    at 240x135 x 8 spp.  Minutes on the CPU for the reference shader, so not regenerated by the CPU suite."""
+    cases = {}
+    classic = rt.scene_classic_cornell()
+    cam = rt.make_camera(512, 512, (0.0, 0.0, 15.5))
+    cases["config1_512x512_spp64_d8"] = (classic, rt.screenshot_uniforms(classic, cam, spp=64, max_bounce=8, env_light=False))
+    sph = rt.scene_textured_sphere()
+    cams = rt.camera_for_box(sph, 240, 135)
+    cases["config2_scene_240x135_spp8_d20"] = (sph, rt.screenshot_uniforms(sph, cams, spp=8, max_bounce=20, env_light=False))
+    return cases

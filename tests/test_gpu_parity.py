@@ -231,6 +231,25 @@ def test_frame_equals_reference_shader_golden(name):
     be.close()
 
 
+@pytest.mark.parametrize("name", sorted(scenes.refshader_big_cases()))
+def test_full_size_frame_equals_reference_shader_crc(name):
+    """BASELINE config 1 at full size (512x512, one 64-spp frame, depth 8) and the 100 368-triangle config-2 scene
+    (240x135, 8 spp, depth 20): every row of the CUDA frame has the CRC the reference's own shader source produced
+    (tests/golden/refshader_big.json, minted by make_golden_refshader.py --big)."""
+    import json
+    import zlib
+    big = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "refshader_big.json")))[name]
+    scene, u = scenes.refshader_big_cases()[name]
+    be = backend(scene, rng_mode=rt.RNG_REF_PCG)
+    be.render_frame(u)
+    img = be.read_frame()
+    be.close()
+    assert list(img.shape) == big["shape"]
+    bad = [y for y in range(img.shape[0]) if (zlib.crc32(img[y].tobytes()) & 0xffffffff) != big["row_crc"][y]]
+    assert not bad, f"{name}: {len(bad)} rows differ from the reference shader, first {bad[:5]}"
+    assert (zlib.crc32(img.tobytes()) & 0xffffffff) == big["crc"]
+
+
 def test_all_material_types_and_env_light():
     """CHECKER, GLASS, partial-smoothness SPECULAR, edge highlight, GLASS_HIGHLIGHT (magenta in trace),
     and the procedural sky on a miss (compute.glsl:216-273, 521-546)."""

@@ -104,3 +104,17 @@ void main()
     i = lines.index("float _rnd0 = random(-0.5f, 0.5f, s);")
     assert lines[i + 1] == "float _rnd1 = random(-0.5f, 0.5f, s);"
     assert lines[i + 2] == "vec3 e = a + xyz(b) * _rnd0 + xyz(c) * _rnd1;"
+
+
+@pytest.mark.parametrize("name", sorted(scenes.refshader_big_cases()))
+def test_oracle_equals_reference_shader_at_full_size(name):
+    """BASELINE config 1 at its full size (512x512, 64 spp, depth 8) and the 100 368-triangle config-2 scene: the
+    oracle's frame against the CRCs the reference shader source produced (tests/golden/refshader_big.json)."""
+    big = json.load(open(os.path.join(GOLD, "refshader_big.json")))[name]
+    scene, u = scenes.refshader_big_cases()[name]
+    img = oracle.OracleScene.from_scene(scene).render_frame(u, rng_mode=rt.RNG_REF_PCG)
+    assert list(img.shape) == big["shape"]
+    rows = [zlib.crc32(img[y].tobytes()) & 0xffffffff for y in range(img.shape[0])]
+    bad = [y for y in range(img.shape[0]) if rows[y] != big["row_crc"][y]]
+    assert not bad, f"{name}: {len(bad)} rows differ from the reference shader, first {bad[:5]}"
+    assert (zlib.crc32(img.tobytes()) & 0xffffffff) == big["crc"]
