@@ -118,3 +118,26 @@ def test_oracle_equals_reference_shader_at_full_size(name):
     bad = [y for y in range(img.shape[0]) if rows[y] != big["row_crc"][y]]
     assert not bad, f"{name}: {len(bad)} rows differ from the reference shader, first {bad[:5]}"
     assert (zlib.crc32(img.tobytes()) & 0xffffffff) == big["crc"]
+
+
+_DATA = "/root/reference/RayTracing/Data"
+
+
+@pytest.mark.skipif(not (refshader.available(True) and os.path.isdir(_DATA)), reason="needs /root/reference and its harness")
+@pytest.mark.parametrize("model,container", [("robot", "cornell"), ("autumn_kitten", "none")])
+def test_real_assets_oracle_equals_reference_shader(model, container):
+    """Shipped models through the folder loader (config 2(i): Data/robot, 25 599 triangles, three textures up to
+    4096²; autumn_kitten carries the isEdgeHighlight / GLASS_HIGHLIGHT materials): oracle frame == shader frame."""
+    s = rt.Scene()
+    s.load_model_folder(os.path.join(_DATA, model))
+    red = s.add_fixed_materials()
+    d = rt.defaults()
+    if container == "cornell":
+        s.add_cornell_box(d.cornell_light_size, d.cornell_padding, red + 3, True)
+    cam = rt.camera_for_box(s, 72, 72)
+    u = rt.screenshot_uniforms(s, cam, spp=4, max_bounce=10, env_light=(container == "none"))
+    img = oracle.OracleScene.from_scene(s).render_frame(u, rng_mode=rt.RNG_REF_PCG)
+    ref = refshader.render(s, u, spec_math=True)
+    diff = bits(img) != bits(ref)
+    assert not diff.any(), f"{model}: {int(diff.sum())} of {diff.size} floats differ"
+    assert np.unique(ref).size > 50
