@@ -499,13 +499,13 @@ __global__ void __launch_bounds__(256) k_emit_nodes(int n, const int32_t* __rest
     const int i = order ? order[src] : src;
     const int32_t pl = cl >= 0 ? (order ? order[cl] : cl) : pack_leaf(~cl, 1);
     const int32_t pr = cr >= 0 ? (order ? order[cr] : cr) : pack_leaf(~cr, 1);
-    // outward rounding with a 1e-3 cell guard band against the rounding of the scaling itself
+    // outward rounding with a guard band (kGuardCells) against the rounding of the scaling itself and of the slab test
     auto qlo = [&](float v, int k) {
-        const float c = floorf((v - grid[k]) * grid[3 + k] - 1e-3f);
+        const float c = floorf((v - grid[k]) * grid[3 + k] - kGuardCells);
         return (uint32_t)fminf(fmaxf(c, 0.0f), 65535.0f);
     };
     auto qhi = [&](float v, int k) {
-        const float c = ceilf((v - grid[k]) * grid[3 + k] + 1e-3f);
+        const float c = ceilf((v - grid[k]) * grid[3 + k] + kGuardCells);
         return (uint32_t)fminf(fmaxf(c, 0.0f), 65535.0f);
     };
     uint4 a, b;

@@ -43,7 +43,16 @@ struct HitRec {
     int32_t slot;  // sorted slot, -1 = miss
 };
 
+#ifndef RT_SLAB_FMA
+#define RT_SLAB_FMA 1
+#endif
 constexpr int kStackSize = 128;
+// outward rounding margin of the quantised planes, in grid cells (bvh_build.cu k_emit_nodes)
+#if RT_SLAB_FMA
+constexpr float kGuardCells = 0.0625f;
+#else
+constexpr float kGuardCells = 1e-3f;
+#endif
 
 // 256-bit read-only global load (sm_100a: LDG.E.ENL2.256.CONSTANT): one instruction, one L1TEX
 // wavefront per lane for 32 bytes, where four 128-bit loads of a 64-byte record would cost four.
@@ -67,8 +76,12 @@ __device__ __forceinline__ float q_hi(uint32_t w) { return __uint_as_float(0x4B0
 
 // The ray in grid coordinates: per-axis scaling of origin and direction leaves t unchanged.
 struct GridRay {
+#if RT_SLAB_FMA
+    float ox, oy, oz;     // -(o - grid_lo) * grid_inv * i: the constant term of t = q * i + c
+#else
     float ox, oy, oz;     // (o - grid_lo) * grid_inv
-    float ix, iy, iz;     // 1 / (d * grid_inv); IEEE: a zero component gives +-inf, NaN drops out of fmin/fmax
+#endif
+    float ix, iy, iz;     // 1 / (d * grid_inv), clamped to +-1e28 (RT_SLAB_FMA=0: a zero component gives +-inf)
 };
 __device__ __forceinline__ GridRay make_grid_ray(const SceneView& sc, V3 o, V3 d) {
     GridRay g;
@@ -78,22 +91,45 @@ __device__ __forceinline__ GridRay make_grid_ray(const SceneView& sc, V3 o, V3 d
     g.ix = 1.0f / (d.x * sc.grid_inv[0]);
     g.iy = 1.0f / (d.y * sc.grid_inv[1]);
     g.iz = 1.0f / (d.z * sc.grid_inv[2]);
+#if RT_SLAB_FMA
+    // finite slopes keep q*i + c free of inf - inf; a ray parallel to a slab then decides by the sign of
+    // (q - o) * 1e28, which the builder's guard band keeps right (kGuardCells)
+    g.ix = fminf(fmaxf(g.ix, -1e28f), 1e28f);
+    g.iy = fminf(fmaxf(g.iy, -1e28f), 1e28f);
+    g.iz = fminf(fmaxf(g.iz, -1e28f), 1e28f);
+    g.ox = -g.ox * g.ix;
+    g.oy = -g.oy * g.iy;
+    g.oz = -g.oz * g.iz;
+#endif
     return g;
 }
-// Two slab tests against the quantised child boxes of one node.  Slabs as (plane - origin) * inv:
-// the subtraction is exact or nearly so, which keeps the test meaningful for rays almost parallel
-// to a slab (an fma of two huge products would cancel catastrophically there; an fma variant with
-// an explicit error bound was measured and lost: 3-register FFMA issues at half rate).  The far
-// side is widened by ~8 ulp so rounding can never cull a true hit.
+__device__ __forceinline__ float slab_t(float q, float o, float i) {
+#if RT_SLAB_FMA
+    return __fmaf_rn(q, i, o);
+#else
+    return (q - o) * i;
+#endif
+}
+// Two slab tests against the quantised child boxes of one node: t = fma(plane, inv, -origin * inv), one FFMA
+// per plane where (plane - origin) * inv needs an FADD and an FMUL (12 fewer instructions per node visit,
+// +2.5 % on config 2).  Conservativeness: with o the origin in cells, the roundings of the grid transform,
+// of the constant term, of the slope and of the fma itself displace a plane by at most
+// 2^-24 * (6|o| + 3 * 65535) cells.  The builder rounds every plane outward by at least kGuardCells = 1/16
+// cell (covers |o| <= 65535, i.e. any origin inside the grid: 0.035 cell) and the far side is widened by
+// 8 ulp relative (covers origins outside it, where |plane - o| grows with |o|), so rounding can never cull
+// a true hit.  Slopes are clamped to +-1e28: no inf - inf for rays parallel to a slab.
+// (RT_SLAB_FMA=0 keeps the subtract-multiply form with a 1e-3 cell guard band.  Selecting near / far planes
+// by direction sign with a byte permute instead of min / max was measured too: 3 more registers cost a
+// resident block per SM and 1.5 %.)
 __device__ __forceinline__ void slab2(const uint32_t (&w)[8], const GridRay& g, float bestT, float& lNear,
                                       float& rNear, bool& hitL, bool& hitR) {
     const float kWiden = 1.000001f;
-    const float lx0 = (q_lo(w[0]) - g.ox) * g.ix, lx1 = (q_hi(w[0]) - g.ox) * g.ix;
-    const float ly0 = (q_lo(w[1]) - g.oy) * g.iy, ly1 = (q_hi(w[1]) - g.oy) * g.iy;
-    const float lz0 = (q_lo(w[2]) - g.oz) * g.iz, lz1 = (q_hi(w[2]) - g.oz) * g.iz;
-    const float rx0 = (q_lo(w[3]) - g.ox) * g.ix, rx1 = (q_hi(w[3]) - g.ox) * g.ix;
-    const float ry0 = (q_lo(w[4]) - g.oy) * g.iy, ry1 = (q_hi(w[4]) - g.oy) * g.iy;
-    const float rz0 = (q_lo(w[5]) - g.oz) * g.iz, rz1 = (q_hi(w[5]) - g.oz) * g.iz;
+    const float lx0 = slab_t(q_lo(w[0]), g.ox, g.ix), lx1 = slab_t(q_hi(w[0]), g.ox, g.ix);
+    const float ly0 = slab_t(q_lo(w[1]), g.oy, g.iy), ly1 = slab_t(q_hi(w[1]), g.oy, g.iy);
+    const float lz0 = slab_t(q_lo(w[2]), g.oz, g.iz), lz1 = slab_t(q_hi(w[2]), g.oz, g.iz);
+    const float rx0 = slab_t(q_lo(w[3]), g.ox, g.ix), rx1 = slab_t(q_hi(w[3]), g.ox, g.ix);
+    const float ry0 = slab_t(q_lo(w[4]), g.oy, g.iy), ry1 = slab_t(q_hi(w[4]), g.oy, g.iy);
+    const float rz0 = slab_t(q_lo(w[5]), g.oz, g.iz), rz1 = slab_t(q_hi(w[5]), g.oz, g.iz);
     lNear = fmaxf(fmaxf(fminf(lx0, lx1), fminf(ly0, ly1)), fmaxf(fminf(lz0, lz1), 0.0f));
     rNear = fmaxf(fmaxf(fminf(rx0, rx1), fminf(ry0, ry1)), fmaxf(fminf(rz0, rz1), 0.0f));
     const float lFar = fminf(fminf(fmaxf(lx0, lx1), fmaxf(ly0, ly1)), fminf(fmaxf(lz0, lz1), bestT)) * kWiden;
