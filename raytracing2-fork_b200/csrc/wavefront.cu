@@ -17,6 +17,8 @@
 // slot owns one float4 of `contrib`; the radiance of a path is a single value written at its
 // terminal event (light hit / miss / error colour), so k_accumulate can add the lanes in sample
 // order and the image does not depend on the order in which paths finish.
+#include <type_traits>
+
 #include "rt_internal.h"
 
 namespace rt {
@@ -275,7 +277,19 @@ struct Stack {
         if (sp < kShStack) { const int2 e = sh[sp * kExtBlock]; c = e.x; t = __int_as_float(e.y); }
         else { c = ovNode[sp - kShStack]; t = ovT[sp - kShStack]; }
     }
+    // DEEP = false: the caller guarantees sp < kShStack (shared entries only, no overflow code at all)
+    template <bool DEEP>
+    __device__ __forceinline__ void pushT(int sp, int32_t c, float t) {
+        if (DEEP) push(sp, c, t);
+        else sh[sp * kExtBlock] = make_int2(c, __float_as_int(t));
+    }
+    template <bool DEEP>
+    __device__ __forceinline__ void getT(int sp, int32_t& c, float& t) const {
+        if (DEEP) { get(sp, c, t); }
+        else { const int2 e = sh[sp * kExtBlock]; c = e.x; t = __int_as_float(e.y); }
+    }
 };
+template <bool DEEP>
 __device__ __forceinline__ void node_step(const SceneView& sc, const RayRegs& r, int32_t& node, int& sp, Stack& st) {
     uint32_t w[8];
     ldg256u(sc.nodes + 2 * node, w);
@@ -283,12 +297,17 @@ __device__ __forceinline__ void node_step(const SceneView& sc, const RayRegs& r,
     bool hitL, hitR;
     slab2(w, r.g, r.bestT, lNear, rNear, hitL, hitR);
     const int32_t cl = (int32_t)w[6], cr = (int32_t)w[7];
-    const bool both = hitL && hitR;
-    const bool goLeft = hitL && (!hitR || lNear <= rNear);
-    const int32_t nearC = goLeft ? cl : cr;
-    if (both) st.push(sp, goLeft ? cr : cl, goLeft ? rNear : lNear);
+    // a missed child is infinitely far: the near / far choice, "both" and "any" then come out of one compare,
+    // one min and one max instead of a predicate ladder
+    const float kFar = 3.0e38f;
+    const float lN = hitL ? lNear : kFar, rN = hitR ? rNear : kFar;
+    const bool goLeft = lN <= rN;
+    const float farT = fmaxf(lN, rN);
+    const bool both = farT < kFar;
+    const bool any = fminf(lN, rN) < kFar;
+    if (both) st.pushT<DEEP>(sp, goLeft ? cr : cl, farT);
     sp += both ? 1 : 0;
-    node = (hitL || hitR) ? nearC : kPop;
+    node = any ? (goLeft ? cl : cr) : kPop;
 }
 
 constexpr int32_t kDrain = (int32_t)0x80000002;     // lane state (SPEC): stack empty, a postponed leaf still to test
@@ -365,6 +384,33 @@ __global__ void __launch_bounds__(kExtBlock) k_extend(const __grid_constant__ Sc
             node = kPop;
         }
     };
+    // one iteration of the node phase for a lane: take the next pending subtree if the lane has none (entries
+    // behind the best hit are dropped), then one node step.  Written with selects, not branches.
+    auto node_iter_impl = [&](auto deepTag, float bestW) {
+        constexpr bool DEEP = decltype(deepTag)::value;
+        if (SPEC) {
+            const bool doPop = (node == kPop) & (sp > 0);
+            sp -= doPop ? 1 : 0;
+            int32_t c = kPop;
+            float tn = 0.0f;
+            if (doPop) st.template getT<DEEP>(sp, c, tn);
+            node = (doPop & (tn <= bestW)) ? c : node;
+            const bool park = is_leaf_code(node) & (post == kNoLeaf);
+            post = park ? node : post;
+            node = park ? kPop : node;
+        }
+        if (node >= 0) {
+            if (COUNT) visits++;
+            node_step<DEEP>(sc, r, node, sp, st);
+            if (SPEC) {
+                const bool park = is_leaf_code(node) & (post == kNoLeaf);
+                post = park ? node : post;
+                node = park ? kPop : node;
+            } else {
+                postpone();
+            }
+        }
+    };
 
     for (;;) {
         // ---- pop phase: lanes that finished a subtree take the next one that can still hold a hit
@@ -429,18 +475,16 @@ __global__ void __launch_bounds__(kExtBlock) k_extend(const __grid_constant__ Sc
                 node = kPop;
             }
         } else {
-            // several node steps per vote amortise the voting overhead
+            // several node steps per vote amortise the voting overhead.  When no lane can reach the end of the
+            // shared part of its stack within this round, the loop without any overflow code runs.
+            const bool deep = __any_sync(FULL, sp + tune.nodeSteps >= kShStack);
+            const float bestW = r.bestT * kWiden;
+            if (!deep) {
 #pragma unroll 1
-            for (int k = 0; k < tune.nodeSteps; k++) {
-                if (SPEC && node == kPop && sp > 0) {
-                    pop_one();
-                    postpone();
-                }
-                if (node >= 0) {
-                    if (COUNT) visits++;
-                    node_step(sc, r, node, sp, st);
-                    postpone();
-                }
+                for (int k = 0; k < tune.nodeSteps; k++) node_iter_impl(std::false_type{}, bestW);
+            } else {
+#pragma unroll 1
+                for (int k = 0; k < tune.nodeSteps; k++) node_iter_impl(std::true_type{}, bestW);
             }
         }
     }
