@@ -343,17 +343,27 @@ def run_gpu(args, rt):
     h2d = ptris.nbytes + pmats.nbytes + sum(p[0].nbytes for p in ptexs) + 192 * frames
     d2h = W * H * 3 if rank == 0 else 0
 
+    phases = {"upload": 0.0, "build": 0.0, "screenshot": 0.0}
+
     def e2e_step():
+        t_a = time.perf_counter()
         be.set_triangles(ptris)
         be.set_materials(pmats)
         for i, (p, _) in enumerate(ptexs):
             be.set_texture(i, p)
+        t_b = time.perf_counter()
         be.build()
-        return be.screenshot(u, frames, want_output=(rank == 0))
+        t_c = time.perf_counter()
+        out = be.screenshot(u, frames, want_output=(rank == 0))
+        t_d = time.perf_counter()
+        phases["upload"] += t_b - t_a; phases["build"] += t_c - t_b; phases["screenshot"] += t_d - t_c
+        return out
 
     e2e_step()
     barrier()
     be.reset_counters()
+    for k in phases:
+        phases[k] = 0.0
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0 = time.perf_counter()
     e0.record(stream)
@@ -439,6 +449,8 @@ def run_gpu(args, rt):
             "segments_per_step": segments / args.steps,
             "e2e": {"value": e2e_value, "unit": "Mrays/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "seconds_per_step": wall / n_e2e, "steps": n_e2e,
+                    "host_phases_ms_per_step": {k: round(v / n_e2e * 1e3, 2) for k, v in phases.items()},
+                    "device_ms_per_step": e0.elapsed_time(e1) / n_e2e,
                     "includes": "rt_scene_set_triangles/materials/texture from pinned host memory, rt_scene_build, "
                                 "rt_screenshot with RGB8 readback"},
             "gpu_launches": int(launches),

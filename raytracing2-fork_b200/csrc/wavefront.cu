@@ -52,13 +52,23 @@ __device__ __forceinline__ Material load_material(const SceneView& sc, int32_t i
 }
 
 // GL_LINEAR / GL_REPEAT / unorm8, no mips (external/OpenGL/textureClass.cpp:95-101); DESIGN.md §4.6
+// b / 255.0f for a byte, bit for bit, without the IEEE division sequence: one Newton correction of the product with
+// the rounded reciprocal is the correctly rounded quotient for every b in 0..255 (checked exhaustively with exact
+// rationals, tests/test_oracle_cpu.py::test_unorm8_reciprocal_sequence_is_exact; the plain product is wrong for 126).
+__device__ __forceinline__ float unorm8(uint8_t b) {
+    const float x = (float)b;
+    const float c = 0.003921568859368563f;  // RN(1 / 255)
+    const float q0 = __fmul_rn(x, c);
+    const float r = __fmaf_rn(-255.0f, q0, x);
+    return __fmaf_rn(r, c, q0);
+}
 __device__ __forceinline__ V3 texel(const uint8_t* __restrict__ px, int w, int ch, int i, int j) {
     const uint8_t* p = px + ((size_t)j * w + i) * ch;
-    const float r = (float)__ldg(p) / 255.0f;
+    const float r = unorm8(__ldg(p));
     if (ch == 1) return v3(r, r, r);
-    const float g = (float)__ldg(p + 1) / 255.0f;
+    const float g = unorm8(__ldg(p + 1));
     if (ch == 2) return v3(r, g, 0.0f);
-    return v3(r, g, (float)__ldg(p + 2) / 255.0f);
+    return v3(r, g, unorm8(__ldg(p + 2)));
 }
 __device__ __forceinline__ V3 sample_texture(const SceneView& sc, int t, float u, float v) {
     const int w = sc.tex_w[t], h = sc.tex_h[t], ch = sc.tex_ch[t];
@@ -71,12 +81,14 @@ __device__ __forceinline__ V3 sample_texture(const SceneView& sc, int t, float u
     const float fy = r * (float)h - 0.5f;
     const float flx = floorf(fx), fly = floorf(fy);
     const float ax = fx - flx, ay = fy - fly;
+    // REPEAT: s, r in [0, 1] put floor(fx) in [-1, w-1] and its right neighbour in [0, w], so the positive modulo
+    // ((i % w) + w) % w of the specification is one conditional add / subtract (eight integer divisions saved)
     int i0 = (int)flx, j0 = (int)fly;
     int i1 = i0 + 1, j1 = j0 + 1;
-    i0 = ((i0 % w) + w) % w;
-    i1 = ((i1 % w) + w) % w;
-    j0 = ((j0 % h) + h) % h;
-    j1 = ((j1 % h) + h) % h;
+    i0 = i0 < 0 ? i0 + w : i0;
+    j0 = j0 < 0 ? j0 + h : j0;
+    i1 = i1 >= w ? i1 - w : i1;
+    j1 = j1 >= h ? j1 - h : j1;
     const uint8_t* px = sc.tex_px[t];
     const float w00 = (1.0f - ax) * (1.0f - ay), w10 = ax * (1.0f - ay), w01 = (1.0f - ax) * ay, w11 = ax * ay;
     return ((texel(px, w, ch, i0, j0) * w00 + texel(px, w, ch, i1, j0) * w10) + texel(px, w, ch, i0, j1) * w01) +
@@ -264,7 +276,10 @@ struct RayRegs {
 // [level][thread], so a warp-wide push or pop is conflict-free (one bank pair per lane) whatever
 // the lanes' depths are; in local memory the same access scatters over up to 32 lines and costs up
 // to 32 L1TEX wavefronts.  Deeper entries (rare: most rays keep fewer than 16 pending nodes) overflow to local memory.
-constexpr int kShStack = 16;
+#ifndef RT_SH_STACK
+#define RT_SH_STACK 16
+#endif
+constexpr int kShStack = RT_SH_STACK;
 struct Stack {
     int2* sh;         // &shared[0][threadIdx.x]; stride kExtBlock
     int32_t* ovNode;  // local overflow

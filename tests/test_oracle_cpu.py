@@ -267,3 +267,41 @@ def test_goldens():
         shot, _ = orc.screenshot(u64, 2, rng_mode=mode)
         want = np.load(os.path.join(GOLDEN, f"classic_shot_64_{name}.npy"))
         assert np.array_equal(shot, want)
+
+
+def test_unorm8_reciprocal_sequence_is_exact():
+    """csrc/wavefront.cu::unorm8 replaces `b / 255.0f` (texel → [0,1], DESIGN.md §4.6) by q0 = b·c, r = fma(−255, q0, b),
+    q = fma(r, c, q0) with c = RN(1/255).  With exact rationals: the result is the correctly rounded quotient for every
+    byte, so no bit of any texel changes (the plain product b·c would be wrong for 126 of the 256 values)."""
+    from fractions import Fraction
+    import math
+
+    def rn32(fr):
+        if fr == 0:
+            return Fraction(0)
+        sign, a = (1, fr) if fr > 0 else (-1, -fr)
+        e = math.floor(math.log2(float(a)))
+        while Fraction(2) ** e > a:
+            e -= 1
+        while Fraction(2) ** (e + 1) <= a:
+            e += 1
+        ulp = Fraction(2) ** (e - 23)
+        q = a / ulp
+        n = q.numerator // q.denominator
+        rem = q - n
+        if rem > Fraction(1, 2) or (rem == Fraction(1, 2) and n % 2 == 1):
+            n += 1
+        return sign * n * ulp
+
+    c = rn32(Fraction(1, 255))
+    assert float(c) == float(np.float32(0.003921568859368563))
+    wrong_plain = 0
+    for b in range(256):
+        x = Fraction(b)
+        q0 = rn32(x * c)
+        r = rn32(x - 255 * q0)
+        q = rn32(q0 + r * c)
+        assert q == rn32(x / 255), b
+        assert float(q) == float(np.float32(b) / np.float32(255.0))
+        wrong_plain += q0 != rn32(x / 255)
+    assert wrong_plain == 126
