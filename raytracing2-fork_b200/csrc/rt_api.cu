@@ -104,6 +104,9 @@ struct rt_ctx {
     int extend_blocks_per_sm = 4;
     int leaf_vote = 12, refill = 8, node_steps = 4;
     int use_ploc = 1, dfs_layout = 1, speculative = 1, shade_blocks_per_sm = 64;
+    int l2_max_persist = -1, l2_max_window = 0;  // device limits, -1 = not queried yet
+    const void* l2_win_base = nullptr;           // the access-policy window currently set on the stream
+    size_t l2_win_bytes = 0;
     uint64_t default_budget = (uint64_t)128 << 20;  // path slots in flight (128 B each = 16 GiB; capped by free memory)
     cudaStream_t own_stream = nullptr;
     cudaStream_t stream = nullptr;
@@ -234,25 +237,31 @@ SceneView make_view(rt_ctx* ctx) {
 // the step 18 % slower), so the window is set only when the whole arena fits the persisting carve-out.
 void apply_l2_window(rt_ctx* ctx) {
     if (!ctx->l2_persist || !ctx->d_bvh.p || ctx->bvh_hot_bytes == 0) return;
-    cudaDeviceProp prop;
-    if (cudaGetDeviceProperties(&prop, ctx->cfg.device) != cudaSuccess || prop.persistingL2CacheMaxSize <= 0) return;
-    if (ctx->bvh_hot_bytes > (size_t)prop.persistingL2CacheMaxSize ||
-        ctx->bvh_hot_bytes > (size_t)prop.accessPolicyMaxWindowSize) {
-        cudaStreamAttrValue off;
-        memset(&off, 0, sizeof off);  // num_bytes = 0 disables a window left by a previous, smaller scene
-        if (cudaStreamSetAttribute(ctx->stream, cudaStreamAttributeAccessPolicyWindow, &off) != cudaSuccess) cudaGetLastError();
-        return;
+    if (ctx->l2_max_persist < 0) {  // device limits, queried once (cudaGetDeviceProperties costs milliseconds)
+        int v = 0;
+        ctx->l2_max_persist = cudaDeviceGetAttribute(&v, cudaDevAttrMaxPersistingL2CacheSize, ctx->cfg.device) == cudaSuccess ? v : 0;
+        ctx->l2_max_window = cudaDeviceGetAttribute(&v, cudaDevAttrMaxAccessPolicyWindowSize, ctx->cfg.device) == cudaSuccess ? v : 0;
+        cudaGetLastError();
     }
-    const size_t carve = std::min<size_t>((size_t)prop.persistingL2CacheMaxSize, ctx->bvh_hot_bytes);
-    cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, carve);
+    if (ctx->l2_max_persist <= 0) return;
+    const bool fits = ctx->bvh_hot_bytes <= (size_t)ctx->l2_max_persist && ctx->bvh_hot_bytes <= (size_t)ctx->l2_max_window;
+    const void* base = fits ? ctx->d_bvh.p : nullptr;
+    const size_t bytes = fits ? ctx->bvh_hot_bytes : 0;
+    // a rebuild of the same scene leaves the window as it is: cudaDeviceSetLimit on the persisting carve-out costs
+    // tens of milliseconds of host time (measured inside bench.py's end-to-end step)
+    if (base == ctx->l2_win_base && bytes == ctx->l2_win_bytes) return;
+    ctx->l2_win_base = base;
+    ctx->l2_win_bytes = bytes;
     cudaStreamAttrValue attr;
-    memset(&attr, 0, sizeof attr);
-    const size_t win = std::min<size_t>(ctx->bvh_hot_bytes, (size_t)prop.accessPolicyMaxWindowSize);
-    attr.accessPolicyWindow.base_ptr = ctx->d_bvh.p;
-    attr.accessPolicyWindow.num_bytes = win;
-    attr.accessPolicyWindow.hitRatio = win > 0 ? (float)std::min(1.0, (double)carve / (double)win) : 0.0f;
-    attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
-    attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+    memset(&attr, 0, sizeof attr);  // num_bytes = 0 disables a window left by a previous, smaller scene
+    if (fits) {
+        cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, bytes);
+        attr.accessPolicyWindow.base_ptr = ctx->d_bvh.p;
+        attr.accessPolicyWindow.num_bytes = bytes;
+        attr.accessPolicyWindow.hitRatio = 1.0f;
+        attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+        attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+    }
     if (cudaStreamSetAttribute(ctx->stream, cudaStreamAttributeAccessPolicyWindow, &attr) != cudaSuccess) cudaGetLastError();
 }
 
@@ -578,6 +587,8 @@ int rt_set_stream(rt_ctx* ctx, void* cuda_stream) {
     GUARD();
     CK(cudaStreamSynchronize(ctx->stream));
     ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
+    ctx->l2_win_base = nullptr;  // the window is a per-stream attribute
+    ctx->l2_win_bytes = 0;
     apply_l2_window(ctx);
     return RT_OK;
 }
