@@ -18,7 +18,7 @@
 //     Karras     : k_hierarchy (one thread per inner node finds its range and split) + k_refit
 //                  (bottom-up AABB union with one atomic flag per inner node); RT_BVH_BUILDER=lbvh
 //   k_emit_nodes   32-byte nodes: both child boxes in the parent, 16-bit planes rounded outward
-//   k_emit_tris    sorted triangle records: (a, e0, e1, N, orig, material) | (uvs, material, orig)
+//   k_emit_tris    sorted triangle records: (a, e0, e1, N, unit normal, material) | (uvs, material, orig)
 // Everything is deterministic (stable sort, min/max are order independent), so every GPU of a
 // multi-GPU job builds the identical tree.
 #include "rt_internal.h"
@@ -537,7 +537,8 @@ __global__ void __launch_bounds__(256) k_emit_tris(const rt_triangle* __restrict
     geom[4 * s + 0] = make_float4(a.x, a.y, a.z, e0.x);
     geom[4 * s + 1] = make_float4(e0.y, e0.z, e1.x, e1.y);
     geom[4 * s + 2] = make_float4(e1.z, N.x, N.y, N.z);
-    geom[4 * s + 3] = make_float4(__int_as_float((int32_t)src), __int_as_float(t.materialIndex), 0.0f, 0.0f);
+    const V3 nrm = normalize(N);  // compute.glsl:331, the very expression k_shade used to evaluate per hit
+    geom[4 * s + 3] = make_float4(nrm.x, nrm.y, nrm.z, __int_as_float(t.materialIndex));
     shade[2 * s + 0] = make_float4(t.aTex[0], t.aTex[1], t.bTex[0], t.bTex[1]);
     shade[2 * s + 1] = make_float4(t.cTex[0], t.cTex[1], __int_as_float(t.materialIndex), __int_as_float((int32_t)src));
     orig[s] = (int32_t)src;

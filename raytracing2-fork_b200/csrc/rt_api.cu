@@ -364,7 +364,11 @@ FrameParams make_params(rt_ctx* ctx, const rt_uniforms& u) {
     fp.width = (int)u.width;
     fp.height = (int)u.height;
     fp.local_pixels = (int)((size_t)u.width * ctx->rows.size());
-    fp.rows = ctx->d_rows.as<int32_t>();
+    const bool tiles = ctx->cfg.split_mode == RT_SPLIT_TILES && ctx->cfg.world_size > 1;
+    fp.rows = tiles ? ctx->d_rows.as<int32_t>() : nullptr;  // identity row table = no table
+    fp.div_pixels = make_fastdiv((uint32_t)fp.local_pixels);
+    fp.div_samples = make_fastdiv(1u);
+    fp.div_width = make_fastdiv((uint32_t)fp.width);
     fp.lanes_active = 1;
     fp.frames_in_batch = 1;
     fp.samples_in_batch = 1;
@@ -404,6 +408,7 @@ int render_frames(rt_ctx* ctx, const rt_uniforms& u, uint32_t first, int stride,
         for (int base = 0; base < spp; base += samples) {
             fp.sample_base = base;
             fp.samples_in_batch = std::min(samples, spp - base);
+            fp.div_samples = make_fastdiv((uint32_t)fp.samples_in_batch);
             fp.lanes_active = fp.frames_in_batch * fp.samples_in_batch;
             CK(wf_render_batch(L, sc, wb, fp));
         }

@@ -42,6 +42,27 @@ struct PathArrays {
     float4* od1;   // dir.yz, throughput.xy
     float4* misc;  // throughput.z, slot id (bits), rng carry (bits), flags (bits: bounce | insideGlass<<16)
 };
+// Exact unsigned division by a launch constant (Granlund & Montgomery): q = (t + ((n - t) >> 1)) >> (l - 1) with
+// t = umulhi(M, n); valid for every 32-bit n and 2 <= d < 2^31.  d == 1 is flagged by l == 0.
+struct FastDiv {
+    uint32_t M, l;
+};
+inline FastDiv make_fastdiv(uint32_t d) {
+    FastDiv f{0u, 0u};
+    if (d <= 1u) return f;
+    uint32_t l = 0;
+    while (((uint64_t)1 << l) < d) l++;
+    f.M = (uint32_t)((((uint64_t)1 << 32) * (((uint64_t)1 << l) - d)) / d + 1);
+    f.l = l;
+    return f;
+}
+#ifdef __CUDACC__
+__device__ __forceinline__ uint32_t fastdiv(uint32_t n, FastDiv f) {
+    if (f.l == 0u) return n;
+    const uint32_t t = __umulhi(f.M, n);
+    return (t + ((n - t) >> 1)) >> (f.l - 1u);
+}
+#endif
 struct FrameParams {
     rt_uniforms u;
     int32_t width, height;
@@ -57,6 +78,9 @@ struct FrameParams {
     int32_t samples_in_batch;   // samples of one pixel of one frame in flight together (1 in RT_RNG_REF_PCG mode)
     int32_t frame_stride;       // frameIndex step between batch frames (world_size under RT_SPLIT_FRAMES)
     const int32_t* rows;        // local row -> absolute row (RT_SPLIT_TILES), NULL = identity
+    FastDiv div_pixels;         // / local_pixels
+    FastDiv div_samples;        // / samples_in_batch
+    FastDiv div_width;          // / width
 };
 struct WaveBuffers {
     PathArrays cur, next;

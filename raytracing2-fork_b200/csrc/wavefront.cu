@@ -154,9 +154,10 @@ __device__ __forceinline__ bool black_checker(V3 p, float scale) {  // S:524-527
     const float m = sum - 2.0f * floorf(sum / 2.0f);
     return m == 0.0f;
 }
-__device__ __forceinline__ V3 tri_normal(const SceneView& sc, int32_t slot) {  // S:331
-    const float4 g2 = __ldg(&sc.tri_geom[4 * slot + 2]);
-    return normalize(v3(g2.y, g2.z, g2.w));
+// normalize(cross(e0, e1)) of S:331, evaluated once per triangle by k_emit_tris with the same operations
+__device__ __forceinline__ V3 tri_normal(const SceneView& sc, int32_t slot) {
+    const float4 g3 = __ldg(&sc.tri_geom[4 * slot + 3]);
+    return v3(g3.x, g3.y, g3.z);
 }
 
 // pixel geometry shared by raygen / first-hit / preview (S:663-676)
@@ -187,9 +188,16 @@ __device__ __forceinline__ void sample_ray(const rt_uniforms& u, const PixelSetu
     d = normalize(endJ - o);
 }
 __device__ __forceinline__ void local_pixel_xy(const FrameParams& fp, int p, int& tx, int& ty) {
-    const int r = p / fp.width;
+    const int r = (int)fastdiv((uint32_t)p, fp.div_width);
     tx = p - r * fp.width;
     ty = fp.rows ? fp.rows[r] : r;
+}
+// tx + ty * W of a local pixel; without a row table (no tile split) that is the local index itself
+__device__ __forceinline__ uint32_t local_pixel_id(const FrameParams& fp, int p) {
+    if (!fp.rows) return (uint32_t)p;
+    int tx, ty;
+    local_pixel_xy(fp, p, tx, ty);
+    return (uint32_t)tx + (uint32_t)ty * fp.u.width;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -627,14 +635,11 @@ __global__ void __launch_bounds__(kBlock, 4) k_shade(const __grid_constant__ Sce
             flags = __float_as_uint(c.w);
             bool insideGlass = (flags >> 16) & 1u;
             const int bounceCount = bounce + 1;  // S:483
-            const int slotLane = slotId / fp.local_pixels;
+            const int slotLane = (int)fastdiv((uint32_t)slotId, fp.div_pixels);
             const int pixLocal = slotId - slotLane * fp.local_pixels;
-            const int batchFrame = fp.frames_in_batch > 1 ? slotLane / fp.samples_in_batch : 0;
-            int tx, ty;
-            local_pixel_xy(fp, pixLocal, tx, ty);
+            const int batchFrame = fp.frames_in_batch > 1 ? (int)fastdiv((uint32_t)slotLane, fp.div_samples) : 0;
             Rng<MODE> rng;
-            rng.init(carry, (uint32_t)tx + (uint32_t)ty * fp.u.width,
-                     fp.u.frameIndex + (uint32_t)(batchFrame * fp.frame_stride), 0u);
+            rng.init(carry, local_pixel_id(fp, pixLocal), fp.u.frameIndex + (uint32_t)(batchFrame * fp.frame_stride), 0u);
             rng.stream((uint32_t)bounceCount);
 
             const int32_t hslot = __float_as_int(h.w);
