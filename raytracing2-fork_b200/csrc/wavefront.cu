@@ -647,9 +647,10 @@ __global__ void __launch_bounds__(kBlock, 4) k_shade(const __grid_constant__ Sce
             V3 radiance = v3(0.0f, 0.0f, 0.0f);
             Material m;
             m.type = -1;
+            float4 g3 = make_float4(0.0f, 0.0f, 0.0f, 0.0f);  // unit normal + material index of the hit triangle
             if (hslot >= 0) {
-                const float4 s1 = __ldg(&sc.tri_shade[2 * hslot + 1]);
-                m = load_material(sc, __float_as_int(s1.z));
+                g3 = __ldg(&sc.tri_geom[4 * hslot + 3]);
+                m = load_material(sc, __float_as_int(g3.w));
             }
             const bool needDir = hslot >= 0 && (m.type == RT_MAT_DIFFUSE || m.type == RT_MAT_TEXTURE ||
                                                 m.type == RT_MAT_SPECULAR || m.type == RT_MAT_CHECKER);
@@ -658,7 +659,7 @@ __global__ void __launch_bounds__(kBlock, 4) k_shade(const __grid_constant__ Sce
             if (hslot >= 0) {
                 const float dst = h.x, bu = h.y, bv = h.z;
                 const V3 hitPoint = o + d * dst;        // S:330
-                const V3 normal = tri_normal(sc, hslot);
+                const V3 normal = v3(g3.x, g3.y, g3.z);  // S:331
                 if (m.type != RT_MAT_GLASS)
                     o = hitPoint - (d * dst) * -1e-3f;  // S:490
                 else
