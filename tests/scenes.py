@@ -99,3 +99,57 @@ def refshader_big_cases():
     cams = rt.camera_for_box(sph, 240, 135)
     cases["config2_scene_240x135_spp8_d20"] = (sph, rt.screenshot_uniforms(sph, cams, spp=8, max_bounce=20, env_light=False))
     return cases
+
+
+def random_scene(seed: int):
+    """A seeded random triangle soup with every material type, up to three small textures of 1, 3 and 4 channels
+    (non-power-of-two sizes), a random camera looking at it, random uniforms.  Returns (scene, uniforms)."""
+    rng = np.random.default_rng(seed)
+    s = rt.Scene()
+    ntex = int(rng.integers(0, 4))
+    for t in range(ntex):
+        ch = (1, 3, 4)[t % 3]
+        w, h = int(rng.integers(3, 20)), int(rng.integers(3, 20))
+        px = rng.integers(0, 256, size=(h, w, ch), dtype=np.uint8)
+        s.set_texture(t, px[:, :, 0] if ch == 1 else px)
+    mats = []
+    for _ in range(int(rng.integers(2, 5))):
+        mats.append(s.add_diffuse(*rng.uniform(0.1, 1.0, 3)))
+    mats.append(s.add_light(*rng.uniform(0.5, 1.0, 3), float(rng.uniform(2.0, 12.0))))
+    mats.append(s.add_specular(rng.uniform(0.2, 1.0, 3), (1, 1, 1), float(rng.uniform(0, 1)), float(rng.uniform(0, 1))))
+    mats.append(s.add_specular((1, 1, 1), (1, 1, 1), 1.0, 1.0))
+    mats.append(s.add_checker(float(rng.uniform(0.5, 3.0))))
+    mats.append(s.add_glass(rng.uniform(0.7, 1.0, 3), float(rng.uniform(1.1, 1.8))))
+    for t in range(ntex):
+        mats.append(s.add_textured(t))
+    mats.append(s.add_textured(ntex))      # texture index out of range: black (compute.glsl:349)
+    m = np.zeros(1, dtype=rt.MATERIAL)
+    m["color"] = (*rng.uniform(0.2, 1.0, 3), 0); m["materialType"] = rt.MAT_DIFFUSE; m["isEdgeHighlight"] = 1; m["textureIndex"] = -1
+    mats.append(s.add_material(m))
+    m2 = np.zeros(1, dtype=rt.MATERIAL)
+    m2["color"] = (1, 1, 0, 0); m2["materialType"] = rt.MAT_GLASS_HIGHLIGHT; m2["textureIndex"] = -1
+    mats.append(s.add_material(m2))
+    n = int(rng.integers(20, 160))
+    tris = np.zeros(n, dtype=rt.TRIANGLE)
+    centre = rng.uniform(-3, 3, size=(n, 3))
+    for k, name in enumerate(("a", "b", "c")):
+        tris[name][:, :3] = (centre + rng.normal(scale=float(rng.uniform(0.3, 1.5)), size=(n, 3))).astype(np.float32)
+    for name in ("aTex", "bTex", "cTex"):
+        tris[name] = rng.uniform(-1.5, 2.5, size=(n, 2)).astype(np.float32)
+    tris["materialIndex"] = rng.choice(mats, size=n)
+    s.add_triangles(tris)
+    # a floor and a big light so that most paths end somewhere
+    s.add_cube((0, -4.5, 0), (14, 0.3, 14), (0, 0, 0), mats[0])
+    s.add_cube((0, 6.0, 0), (5, 0.2, 5), (0, 0, 0), mats[int(np.flatnonzero(s.materials["materialType"][mats] == rt.MAT_LIGHT)[0])])
+    pos = rng.uniform(-1, 1, 3) * (2.0, 1.5, 2.0) + (0.0, 0.5, 11.0)
+    cam = rt.make_camera(int(rng.integers(24, 56)), int(rng.integers(16, 40)), tuple(float(x) for x in pos),
+                         pitch=float(rng.uniform(-0.15, 0.15)), yaw=float(np.pi / 2 + rng.uniform(-0.2, 0.2)),
+                         defocus=float(rng.choice([0.0, 0.0, 0.03])))
+    if rng.random() < 0.25:
+        u = rt.interactive_uniforms(s, cam)
+        u["basicShadingShadow"] = int(rng.integers(0, 2))
+    else:
+        u = rt.screenshot_uniforms(s, cam, spp=int(rng.integers(1, 7)), max_bounce=int(rng.integers(1, 14)),
+                                   env_light=bool(rng.integers(0, 2)))
+        u["frameIndex"] = int(rng.integers(0, 1000))
+    return s, u

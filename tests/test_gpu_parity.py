@@ -250,6 +250,23 @@ def test_full_size_frame_equals_reference_shader_crc(name):
     assert (zlib.crc32(img.tobytes()) & 0xffffffff) == big["crc"]
 
 
+@pytest.mark.parametrize("seed", range(20))
+def test_fuzz_frames_equal_oracle(seed):
+    """Seeded random triangle soups (tests/scenes.py::random_scene — the same ones the CPU suite checks against the
+    reference shader): CUDA frame == oracle frame in both RNG modes, and 2 000 random rays agree on id, dst, u, v."""
+    scene, u = scenes.random_scene(seed)
+    orc = oracle.OracleScene.from_scene(scene)
+    for mode in (rt.RNG_REF_PCG, rt.RNG_PHILOX):
+        be = backend(scene, rng_mode=mode)
+        be.render_frame(u)
+        assert_image_equal(be.read_frame(), orc.render_frame(u, rng_mode=mode), f"random scene {seed} mode {mode}")
+        if mode == rt.RNG_PHILOX:
+            o, d = random_rays(2000, seed, -5.0, 5.0)
+            a, b = be.trace_rays(o, d), orc.trace_rays(o, d, use_bvh=False)
+            assert np.array_equal(a[0], b[0]) and all(np.array_equal(bits(x), bits(y)) for x, y in zip(a[1:], b[1:]))
+        be.close()
+
+
 def test_all_material_types_and_env_light():
     """CHECKER, GLASS, partial-smoothness SPECULAR, edge highlight, GLASS_HIGHLIGHT (magenta in trace),
     and the procedural sky on a miss (compute.glsl:216-273, 521-546)."""

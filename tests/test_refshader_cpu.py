@@ -141,3 +141,17 @@ def test_real_assets_oracle_equals_reference_shader(model, container):
     diff = bits(img) != bits(ref)
     assert not diff.any(), f"{model}: {int(diff.sum())} of {diff.size} floats differ"
     assert np.unique(ref).size > 50
+
+
+@pytest.mark.skipif(not refshader.available(True), reason="oracle/_ref/libref_shader.so not built (needs /root/reference)")
+@pytest.mark.parametrize("seed", range(64))
+def test_fuzz_oracle_equals_reference_shader(seed):
+    """Seeded random triangle soups (every material type, 1/3/4-channel non-power-of-two textures, out-of-range
+    texture index, defocus, sky on/off, previews, random frameIndex): oracle frame == reference shader frame."""
+    scene, u = scenes.random_scene(seed)
+    img = oracle.OracleScene.from_scene(scene).render_frame(u, rng_mode=rt.RNG_REF_PCG)
+    ref = refshader.render(scene, u, spec_math=True)
+    diff = bits(img) != bits(ref)
+    nan_both = np.isnan(img) & np.isnan(ref)
+    assert not (diff & ~nan_both).any(), f"seed {seed}: {int((diff & ~nan_both).sum())} of {diff.size} floats differ"
+    assert np.unique(ref[..., :3]).size > 2   # not a blank image
