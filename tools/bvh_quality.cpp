@@ -96,6 +96,27 @@ static float trace(const Bvh& b, V o, V d, Stats& st, int& hitTriIdx) { V inv{1 
     bool got = false; while (sp > 0) { --sp; if (ts[sp] <= best) { cur = stack[sp]; got = true; break; } } if (!got) break; }
   return best; }
 
+
+// ---- wide BVH (round-2 costing): collapse a BVH2 into k-wide nodes by repeatedly opening the child with the
+// largest surface area; ordered traversal (children sorted by entry distance, far ones pushed).
+struct WNode { int n = 0; int child[8]; Box box[8]; };  // child >= 0: wide node, < 0: ~leaf-node index of the BVH2
+struct WBvh { std::vector<WNode> nodes; };
+static WBvh collapse(const Bvh& b, int width) { WBvh w; w.nodes.reserve(b.nodes.size() / 2);
+  std::function<int(int)> rec = [&](int root2) -> int { int id = (int)w.nodes.size(); w.nodes.push_back(WNode()); std::vector<int> slots{b.nodes[root2].left, b.nodes[root2].right};
+    for (;;) { if ((int)slots.size() >= width) break; int best = -1; float ba = -1; for (size_t i = 0; i < slots.size(); i++) if (!b.nodes[slots[i]].count) { float a = b.nodes[slots[i]].box.area(); if (a > ba) { ba = a; best = (int)i; } }
+      if (best < 0) break; int open = slots[best]; slots[best] = b.nodes[open].left; slots.push_back(b.nodes[open].right); }
+    WNode nd; nd.n = (int)slots.size(); for (int i = 0; i < nd.n; i++) { nd.box[i] = b.nodes[slots[i]].box; nd.child[i] = b.nodes[slots[i]].count ? ~slots[i] : 0; }
+    w.nodes[id] = nd; for (int i = 0; i < nd.n; i++) if (!b.nodes[slots[i]].count) { int c = rec(slots[i]); w.nodes[id].child[i] = c; } return id; };
+  rec(b.root); return w; }
+struct WStats { double visits = 0, boxes = 0, tris = 0, pushes = 0; };
+static void traceWide(const Bvh& b, const WBvh& w, V o, V d, WStats& st) { V inv{1 / d.x, 1 / d.y, 1 / d.z}; float best = 1e30f; int stack[256]; float ts[256]; int sp = 0; int cur = 0;
+  for (;;) { if (cur >= 0) { const WNode& n = w.nodes[cur]; st.visits++; st.boxes += n.n; int idx[8]; float tn[8]; int h = 0;
+      for (int i = 0; i < n.n; i++) { float t; if (slab(n.box[i], o, inv, best, t)) { int k = h++; while (k > 0 && tn[k - 1] > t) { tn[k] = tn[k - 1]; idx[k] = idx[k - 1]; k--; } tn[k] = t; idx[k] = i; } }
+      for (int k = h - 1; k >= 1; k--) { stack[sp] = n.child[idx[k]]; ts[sp++] = tn[k]; st.pushes++; }
+      if (h) { cur = n.child[idx[0]]; continue; } }
+    else { const Node& l = b.nodes[~cur]; for (int i = l.first; i < l.first + l.count; i++) { st.tris++; float dst; if (hitTri(tris[b.order[i]], o, d, dst) && dst < best) best = dst; } }
+    bool got = false; while (sp > 0) { --sp; if (ts[sp] <= best) { cur = stack[sp]; got = true; break; } } if (!got) break; } }
+
 int main(int argc, char** argv) { if (argc < 2) return 2; FILE* f = fopen(argv[1], "rb"); int64_t hdr[8]; if (!f || fread(hdr, 8, 8, f) != 8) return 1; int n = (int)hdr[1]; std::vector<float> raw((size_t)n * 20); if (fread(raw.data(), 80, n, f) != (size_t)n) return 1; fclose(f);
   tris.resize(n); tb.resize(n); cen.resize(n); for (int i = 0; i < n; i++) { float* p = &raw[(size_t)i * 20]; tris[i] = {{p[0], p[1], p[2]}, {p[4], p[5], p[6]}, {p[8], p[9], p[10]}}; tb[i].grow(tris[i].a); tb[i].grow(tris[i].b); tb[i].grow(tris[i].c); cen[i] = (tb[i].lo + tb[i].hi) * 0.5f; }
   // rays: diffuse bounces — start on a random triangle (area-agnostic: via a primary hit from a random interior point), cosine-ish direction
@@ -106,4 +127,6 @@ int main(int argc, char** argv) { if (argc < 2) return 2; FILE* f = fopen(argv[1
     V r; do { r = {U(rng) * 2 - 1, U(rng) * 2 - 1, U(rng) * 2 - 1}; } while (dot(r, r) >= 1); r = r * (1 / std::sqrt(dot(r, r))); V nd = N + r; float nl = std::sqrt(dot(nd, nd)); if (nl < 1e-4f) continue; ro.push_back(p); rd.push_back(nd * (1 / nl)); }
   auto eval = [&](const char* name, const Bvh& b) { Stats st; int ti; for (size_t i = 0; i < ro.size(); i++) trace(b, ro[i], rd[i], st, ti); printf("%-12s nodes %8zu depth %3d SAH %8.2f  node visits/ray %7.2f  tri tests/ray %6.2f\n", name, b.nodes.size(), depthOf(b, b.root), sahCost(b), st.nodes / ro.size(), st.tris / ro.size()); fflush(stdout); };
   eval("binned SAH", ref); { Bvh l = buildLBVH(); eval("LBVH", l); } for (int r : {10, 25}) { char nm[32]; snprintf(nm, 32, "PLOC r=%d", r); Bvh p = buildPLOC(r); eval(nm, p); if (r == 10) { for (int k = 0; k < 3; k++) { rotate(p, 2); snprintf(nm, 32, "PLOC+rot%d", 2 * (k + 1)); eval(nm, p); } } }
+  { Bvh p = buildPLOC(10); for (int width : {2, 4, 8}) { WBvh w = collapse(p, width); WStats st; for (size_t i = 0; i < ro.size(); i++) traceWide(p, w, ro[i], rd[i], st); double m = (double)ro.size();
+      printf("PLOC -> BVH%d  wide nodes %8zu  visits/ray %6.2f  box tests/ray %6.2f  pushes/ray %5.2f  tri tests/ray %5.2f\n", width, w.nodes.size(), st.visits / m, st.boxes / m, st.pushes / m, st.tris / m); fflush(stdout); } }
   return 0; }
