@@ -521,6 +521,87 @@ __global__ void __launch_bounds__(256) k_emit_nodes(int n, const int32_t* __rest
     nodes[2 * i + 1] = b;
 }
 
+// ---------------------------------------------------------------------------------------------
+// 4-wide nodes, collapsed from the binary tree level by level: every queue entry (binary inner node, wide index)
+// starts from the node's two children and opens, at most twice, the inner child with the largest surface area.
+// Inner slots get a wide index and go to the next level's queue; leaf slots keep their packed leaf code; unused
+// slots carry the degenerate box at the far grid corner and the leaf code of triangle 0 (the slab test orders each
+// plane pair itself, so no box is unhittable; a ray through that corner merely tests one triangle more).
+// 64 bytes per node = 4 x (3 words of lo | hi << 16) + 4 children.
+// Numbering depends on atomics (topology does not), which is harmless: the closest-hit rule makes the image
+// independent of the hierarchy's layout.
+__global__ void __launch_bounds__(256) k_collapse4(int n, const int32_t* __restrict__ children,
+                                                   const float4* __restrict__ boxes, const float* __restrict__ grid,
+                                                   const int2* __restrict__ qin, const uint32_t* __restrict__ qinCount,
+                                                   int2* __restrict__ qout, uint32_t* __restrict__ qoutCount,
+                                                   uint32_t* __restrict__ wideCount, uint4* __restrict__ nodes4) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= *qinCount) return;
+    const int2 e = qin[i];
+    int32_t slot[4] = {children[2 * e.x], children[2 * e.x + 1], -1, -1};
+    int cnt = 2;
+    auto ent = [&](int32_t c) { return c >= 0 ? c : (n - 1 + ~c); };
+    auto area = [&](int32_t c) {
+        const float4 lo = boxes[2 * ent(c)], hi = boxes[2 * ent(c) + 1];
+        const float dx = hi.x - lo.x, dy = hi.y - lo.y, dz = hi.z - lo.z;
+        return dx * dy + dy * dz + dz * dx;
+    };
+    for (int round = 0; round < 2; round++) {
+        int best = -1;
+        float bestA = -1.0f;
+        for (int k = 0; k < cnt; k++)
+            if (slot[k] >= 0) {
+                const float a = area(slot[k]);
+                if (a > bestA) { bestA = a; best = k; }
+            }
+        if (best < 0) break;
+        const int32_t open = slot[best];
+        slot[best] = children[2 * open];
+        slot[cnt++] = children[2 * open + 1];
+    }
+    auto qlo = [&](float v, int k) {
+        const float c = floorf((v - grid[k]) * grid[3 + k] - kGuardCells);
+        return (uint32_t)fminf(fmaxf(c, 0.0f), 65535.0f);
+    };
+    auto qhi = [&](float v, int k) {
+        const float c = ceilf((v - grid[k]) * grid[3 + k] + kGuardCells);
+        return (uint32_t)fminf(fmaxf(c, 0.0f), 65535.0f);
+    };
+    uint32_t w[16];
+    for (int k = 0; k < 4; k++) {
+        if (k < cnt) {
+            const float4 lo = boxes[2 * ent(slot[k])], hi = boxes[2 * ent(slot[k]) + 1];
+            w[3 * k + 0] = qlo(lo.x, 0) | (qhi(hi.x, 0) << 16);
+            w[3 * k + 1] = qlo(lo.y, 1) | (qhi(hi.y, 1) << 16);
+            w[3 * k + 2] = qlo(lo.z, 2) | (qhi(hi.z, 2) << 16);
+            int32_t ref;
+            if (slot[k] >= 0) {
+                ref = (int32_t)atomicAdd(wideCount, 1u);
+                qout[atomicAdd(qoutCount, 1u)] = make_int2(slot[k], ref);
+            } else {
+                ref = pack_leaf(~slot[k], 1);
+            }
+            w[12 + k] = (uint32_t)ref;
+        } else {
+            w[3 * k + 0] = w[3 * k + 1] = w[3 * k + 2] = 0xffffffffu;  // lo = hi = 65535
+            w[12 + k] = (uint32_t)pack_leaf(0, 1);
+        }
+    }
+    uint4* dst = nodes4 + 4 * (size_t)e.y;
+    dst[0] = make_uint4(w[0], w[1], w[2], w[3]);
+    dst[1] = make_uint4(w[4], w[5], w[6], w[7]);
+    dst[2] = make_uint4(w[8], w[9], w[10], w[11]);
+    dst[3] = make_uint4(w[12], w[13], w[14], w[15]);
+}
+__global__ void k_collapse_init(int2* q, uint32_t* counters) {
+    if (threadIdx.x == 0) {
+        q[0] = make_int2(0, 0);  // the binary root becomes wide node 0
+        counters[0] = 1u;        // wide nodes allocated
+        counters[1] = 1u;        // entries in queue A
+        counters[2] = 0u;        // entries in queue B
+    }
+}
+
 // Sorted triangle records.  e0, e1 and N are computed with exactly the operations of
 // compute.glsl:307-309 (and -fmad=false), so precomputing them changes no bit of any hit.
 __global__ void __launch_bounds__(256) k_emit_tris(const rt_triangle* __restrict__ tris,
@@ -619,6 +700,26 @@ cudaError_t build_lbvh(const BuildArgs& a, cudaStream_t st, uint64_t* launches) 
     }
     k_grid<<<1, 32, 0, st>>>(a.bounds, a.grid); L++;
     if (n >= 2) { k_emit_nodes<<<nb(n - 1, 256), 256, 0, st>>>(n, a.children, a.boxes, a.grid, order, a.nodes); L++; }
+    if (n >= 2 && a.nodes4) {
+        // queues in the two key buffers of the sort (n int2 each, dead by now); counters in the histogram buffer
+        int2* q[2] = {reinterpret_cast<int2*>(a.keys[0]), reinterpret_cast<int2*>(a.keys[1])};
+        uint32_t* counters = a.hist;  // [0] wide nodes, [1] |queue A|, [2] |queue B|
+        k_collapse_init<<<1, 32, 0, st>>>(q[0], counters); L++;
+        uint32_t level = 1;
+        int cur = 0, levels = 0;
+        while (level > 0) {
+            levels++;
+            k_collapse4<<<nb((int)level, 256), 256, 0, st>>>(n, a.children, a.boxes, a.grid, q[cur], counters + 1 + cur,
+                                                             q[cur ^ 1], counters + 1 + (cur ^ 1), counters, a.nodes4); L++;
+            cudaMemsetAsync(counters + 1 + cur, 0, sizeof(uint32_t), st);  // this queue is the next level's output
+            cudaMemcpyAsync(&level, counters + 1 + (cur ^ 1), sizeof(uint32_t), cudaMemcpyDeviceToHost, st);
+            cudaError_t e = cudaStreamSynchronize(st);
+            if (e != cudaSuccess) return e;
+            cur ^= 1;
+        }
+        cudaMemcpyAsync(a.wide_count, counters, sizeof(uint32_t), cudaMemcpyDeviceToDevice, st);
+        if (a.wide_levels) *a.wide_levels = levels;
+    }
     k_emit_tris<<<nb(n, 256), 256, 0, st>>>(a.tris, a.vals[0], n, a.geom, a.shade, a.orig); L++;
     if (launches) *launches += L;
     return cudaGetLastError();

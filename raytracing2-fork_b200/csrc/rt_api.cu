@@ -103,7 +103,13 @@ struct rt_ctx {
     int sm_count = 148;
     int extend_blocks_per_sm = 4;
     int leaf_vote = 12, refill = 8, node_steps = 4;
+    int node_steps_wide = 2, extend_blocks_per_sm_wide = 8;
     int use_ploc = 1, dfs_layout = 1, speculative = 1, shade_blocks_per_sm = 64;
+    int bvh_width = 4;             // 4: k_extend walks 4-wide nodes collapsed from the binary tree; 2: the binary tree (RT_BVH_WIDTH)
+    DevBuf d_nodes4, d_wide_count;
+    uint32_t wide_nodes = 0;
+    int wide_depth = 0;
+    bool wide_ok = false;          // 4-wide nodes built and the stack bound (3 pushes per level) holds
     int l2_max_persist = -1, l2_max_window = 0;  // device limits, -1 = not queried yet
     const void* l2_win_base = nullptr;           // the access-policy window currently set on the stream
     size_t l2_win_bytes = 0;
@@ -191,6 +197,8 @@ Launcher make_launcher(rt_ctx* ctx) {
     L.rng_mode = ctx->cfg.rng_mode;
     L.instrument = ctx->cfg.instrument != 0;
     L.extend_grid = ctx->sm_count * ctx->extend_blocks_per_sm;
+    L.extend_grid_wide = ctx->sm_count * ctx->extend_blocks_per_sm_wide;
+    L.node_steps_wide = ctx->node_steps_wide;
     L.leaf_vote = ctx->leaf_vote;
     L.refill = ctx->refill;
     L.node_steps = ctx->node_steps;
@@ -210,6 +218,7 @@ SceneView make_view(rt_ctx* ctx) {
     SceneView v;
     memset(&v, 0, sizeof v);
     v.nodes = ctx->p_nodes;
+    v.nodes4 = ctx->wide_ok ? ctx->d_nodes4.as<uint4>() : nullptr;
     for (int k = 0; k < 3; k++) {
         v.grid_lo[k] = ctx->grid[k];
         v.grid_inv[k] = ctx->grid[3 + k];
@@ -534,7 +543,8 @@ int rt_create(rt_ctx** out, const rt_config* cfg) {
         return fail(nullptr, RT_ERR_CUDA, m);
     }
     ctx->stream = ctx->own_stream;
-    ctx->extend_blocks_per_sm = wf_extend_blocks_per_sm(cfg->instrument != 0);
+    ctx->extend_blocks_per_sm = wf_extend_blocks_per_sm(cfg->instrument != 0, false);
+    ctx->extend_blocks_per_sm_wide = wf_extend_blocks_per_sm(cfg->instrument != 0, true);
     {
         // Path slots: fewer, larger wavefronts amortise the drain of the persistent kernels (config 2: 8 lanes
         // per pixel 1203 ms/step, 64 lanes 1057 ms).  HBM is there to be used: default 128 Mi slots = 16 GiB,
@@ -552,9 +562,11 @@ int rt_create(rt_ctx** out, const rt_config* cfg) {
     if (const char* e8 = getenv("RT_MAX_PATHS_MI")) ctx->default_budget = (uint64_t)std::max(1, atoi(e8)) << 20;
     if (const char* e7 = getenv("RT_EXT_SPEC")) ctx->speculative = atoi(e7);
     if (const char* e6 = getenv("RT_BVH_LAYOUT")) ctx->dfs_layout = strcmp(e6, "creation") != 0;
+    if (const char* e9 = getenv("RT_BVH_WIDTH")) ctx->bvh_width = atoi(e9) == 4 ? 4 : 2;
     if (const char* e5 = getenv("RT_BVH_BUILDER")) ctx->use_ploc = strcmp(e5, "lbvh") != 0;
     if (const char* e4 = getenv("RT_EXT_NODE_STEPS")) ctx->node_steps = std::max(1, std::min(16, atoi(e4)));
-    if (const char* e3 = getenv("RT_EXT_BLOCKS_PER_SM")) ctx->extend_blocks_per_sm = std::max(1, std::min(32, atoi(e3)));
+    if (const char* e3 = getenv("RT_EXT_BLOCKS_PER_SM")) ctx->extend_blocks_per_sm = ctx->extend_blocks_per_sm_wide = std::max(1, std::min(32, atoi(e3)));
+    if (const char* e10 = getenv("RT_EXT_NODE_STEPS_WIDE")) ctx->node_steps_wide = std::max(1, std::min(4, atoi(e10)));
     if (ctx->d_stats.reserve(4 * sizeof(unsigned long long)) != cudaSuccess ||
         cudaMemsetAsync(ctx->d_stats.p, 0, 4 * sizeof(unsigned long long), ctx->stream) != cudaSuccess) {
         delete ctx;
@@ -700,6 +712,16 @@ int rt_scene_build(rt_ctx* ctx) {
     a.nodeDepth = ctx->d_node_depth.as<uint32_t>();
     a.maxDepth = ctx->d_depth.as<uint32_t>();
     a.nodes = ctx->p_nodes;
+    a.nodes4 = nullptr;
+    a.wide_count = nullptr;
+    int wideLevels = 0;
+    a.wide_levels = &wideLevels;
+    if (ctx->bvh_width == 4 && n >= 2) {
+        CK(ctx->d_nodes4.reserve(nn * 4 * sizeof(uint4)));
+        CK(ctx->d_wide_count.reserve(sizeof(uint32_t)));
+        a.nodes4 = ctx->d_nodes4.as<uint4>();
+        a.wide_count = ctx->d_wide_count.as<uint32_t>();
+    }
     a.grid = ctx->d_grid.as<float>();
     a.geom = ctx->p_geom;
     a.shade = ctx->p_shade;
@@ -713,6 +735,7 @@ int rt_scene_build(rt_ctx* ctx) {
     uint32_t depth = 0;
     CK(cudaMemcpyAsync(&depth, ctx->d_depth.p, sizeof depth, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaMemcpyAsync(ctx->grid, ctx->d_grid.p, sizeof ctx->grid, cudaMemcpyDeviceToHost, ctx->stream));
+    if (a.wide_count) CK(cudaMemcpyAsync(&ctx->wide_nodes, a.wide_count, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     float ms = 0.0f;
     cudaEventElapsedTime(&ms, e0, e1);
@@ -732,6 +755,9 @@ int rt_scene_build(rt_ctx* ctx) {
     }
     if ((int)depth + 1 >= kStackSize)
         return fail(ctx, RT_ERR_INVALID, "rt_scene_build: BVH deeper than the traversal stack (" + std::to_string(depth) + ")");
+    // a 4-wide visit pushes up to three children: the worst-case stack is 3 x (depth of the wide tree)
+    ctx->wide_ok = a.nodes4 != nullptr && wideLevels > 0 && 3 * (wideLevels + 1) < kStackSize;
+    ctx->wide_depth = wideLevels;
     ctx->built = true;
     apply_l2_window(ctx);
     return RT_OK;
@@ -930,6 +956,11 @@ int rt_get_counters(rt_ctx* ctx, rt_counters* out) {
     out->bvh_nodes = ctx->n_tris >= 2 ? (uint64_t)ctx->n_tris - 1 : 0;
     out->bvh_bytes = out->bvh_nodes * 32 + (uint64_t)ctx->n_tris * 48;
     out->bvh_depth = ctx->bvh_depth;
+    if (ctx->wide_ok) {  // what k_extend walks: the 4-wide tree
+        out->bvh_nodes = ctx->wide_nodes;
+        out->bvh_bytes = (uint64_t)ctx->wide_nodes * 64 + (uint64_t)ctx->n_tris * 48;
+        out->bvh_depth = (uint64_t)ctx->wide_depth;
+    }
     return RT_OK;
 }
 

@@ -27,6 +27,9 @@ struct BuildArgs {
     uint32_t* maxDepth;       // 1
     float* grid;              // 6: quantisation grid (output)
     uint4* nodes;             // 2*(n-1)   (output)
+    uint4* nodes4;            // 4*(n-1) or NULL: 4-wide nodes collapsed from the binary tree (output)
+    uint32_t* wide_count;     // 1: number of 4-wide nodes written (output, device)
+    int* wide_levels;         // host: depth of the 4-wide tree = levels the collapse ran (output)
     float4* geom;             // 4*n       (output)
     float4* shade;            // 2*n       (output)
     int32_t* orig;            // n         (output)
@@ -102,6 +105,8 @@ struct Launcher {
     int rng_mode;
     bool instrument;
     int extend_grid;   // persistent k_extend grid: SMs x resident blocks per SM
+    int extend_grid_wide;  // the same for the 4-wide variant (more registers)
+    int node_steps_wide;   // node steps per vote of the 4-wide variant
     int leaf_vote;     // k_extend: leaf step when this many lanes wait at a leaf
     int refill;        // k_extend: refill when this many lanes are idle
     int node_steps;    // k_extend: node steps per vote
@@ -117,7 +122,7 @@ struct Launcher {
     bool timing;
 };
 
-int wf_extend_blocks_per_sm(bool instrument);
+int wf_extend_blocks_per_sm(bool instrument, bool wide);
 cudaError_t wf_clear_accum(const Launcher& L, const WaveBuffers& wb, long long entries);
 cudaError_t wf_seed_pixels(const Launcher& L, const SceneView& sc, const WaveBuffers& wb, const FrameParams& fp);
 cudaError_t wf_render_batch(const Launcher& L, const SceneView& sc, const WaveBuffers& wb, const FrameParams& fp);

@@ -24,6 +24,7 @@ namespace rt {
 
 struct SceneView {
     const uint4* __restrict__ nodes;       // 2 per inner node (32 B, 32-byte aligned)
+    const uint4* __restrict__ nodes4;      // 4 per 4-wide node (64 B), or NULL (RT_BVH_WIDTH=4 builds them for k_extend)
     const float4* __restrict__ tri_geom;   // 4 per sorted triangle (64 B, 32-byte aligned)
     const float4* __restrict__ tri_shade;  // 2 per sorted triangle
     const int32_t* __restrict__ tri_orig;
@@ -136,6 +137,17 @@ __device__ __forceinline__ void slab2(const uint32_t (&w)[8], const GridRay& g, 
     const float rFar = fminf(fminf(fmaxf(rx0, rx1), fmaxf(ry0, ry1)), fminf(fmaxf(rz0, rz1), bestT)) * kWiden;
     hitL = lNear <= lFar;
     hitR = rNear <= rFar;
+}
+// One slab test against a quantised box (words lo | hi << 16 per axis): entry distance, or kSlabMiss.
+constexpr float kSlabMiss = 3.0e38f;
+__device__ __forceinline__ float slab1(uint32_t wx, uint32_t wy, uint32_t wz, const GridRay& g, float bestT) {
+    const float kWiden = 1.000001f;
+    const float x0 = slab_t(q_lo(wx), g.ox, g.ix), x1 = slab_t(q_hi(wx), g.ox, g.ix);
+    const float y0 = slab_t(q_lo(wy), g.oy, g.iy), y1 = slab_t(q_hi(wy), g.oy, g.iy);
+    const float z0 = slab_t(q_lo(wz), g.oz, g.iz), z1 = slab_t(q_hi(wz), g.oz, g.iz);
+    const float tn = fmaxf(fmaxf(fminf(x0, x1), fminf(y0, y1)), fmaxf(fminf(z0, z1), 0.0f));
+    const float tf = fminf(fminf(fmaxf(x0, x1), fmaxf(y0, y1)), fminf(fmaxf(z0, z1), bestT)) * kWiden;
+    return tn <= tf ? tn : kSlabMiss;
 }
 // first 48 bytes of a triangle record: a, e0, e1, N
 struct TriGeom {

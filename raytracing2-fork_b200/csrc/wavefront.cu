@@ -333,6 +333,37 @@ __device__ __forceinline__ void node_step(const SceneView& sc, const RayRegs& r,
     node = any ? (goLeft ? cl : cr) : kPop;
 }
 
+// The same step over a 4-wide node (64 bytes, two 256-bit loads): four slab tests, a 5-comparator sorting network
+// on (entry distance, child) with missed children at +inf, the nearest child becomes the lane's node and the other
+// hit children are pushed farthest first.  Up to three pushes per step.
+template <bool DEEP>
+__device__ __forceinline__ void node_step4(const SceneView& sc, const RayRegs& r, int32_t& node, int& sp, Stack& st) {
+    uint32_t a[8], b[8];
+    ldg256u(sc.nodes4 + 4 * node, a);
+    ldg256u(sc.nodes4 + 4 * node + 2, b);
+    float t[4];
+    int32_t c[4] = {(int32_t)b[4], (int32_t)b[5], (int32_t)b[6], (int32_t)b[7]};
+    t[0] = slab1(a[0], a[1], a[2], r.g, r.bestT);
+    t[1] = slab1(a[3], a[4], a[5], r.g, r.bestT);
+    t[2] = slab1(a[6], a[7], b[0], r.g, r.bestT);
+    t[3] = slab1(b[1], b[2], b[3], r.g, r.bestT);
+#define RT_CE(i, j)                                   \
+    {                                                 \
+        const bool sw = t[j] < t[i];                  \
+        const float lo = fminf(t[i], t[j]);           \
+        const float hi = fmaxf(t[i], t[j]);           \
+        const int32_t ci = sw ? c[j] : c[i];          \
+        const int32_t cj = sw ? c[i] : c[j];          \
+        t[i] = lo; t[j] = hi; c[i] = ci; c[j] = cj;   \
+    }
+    RT_CE(0, 1) RT_CE(2, 3) RT_CE(0, 2) RT_CE(1, 3) RT_CE(1, 2)
+#undef RT_CE
+    if (t[3] < kSlabMiss) { st.pushT<DEEP>(sp, c[3], t[3]); sp++; }
+    if (t[2] < kSlabMiss) { st.pushT<DEEP>(sp, c[2], t[2]); sp++; }
+    if (t[1] < kSlabMiss) { st.pushT<DEEP>(sp, c[1], t[1]); sp++; }
+    node = t[0] < kSlabMiss ? c[0] : kPop;
+}
+
 constexpr int32_t kDrain = (int32_t)0x80000002;     // lane state (SPEC): stack empty, a postponed leaf still to test
 constexpr int32_t kNoLeaf = (int32_t)0x80000003;    // `post` holds no leaf
 __device__ __forceinline__ bool is_leaf_code(int32_t x) { return x < 0 && (uint32_t)x > (uint32_t)kNoLeaf; }
@@ -341,7 +372,7 @@ __device__ __forceinline__ bool is_leaf_code(int32_t x) { return x < 0 && (uint3
 // `post` and keeps descending; it only has to wait for a leaf step when it reaches a SECOND leaf (or runs
 // out of nodes).  Node steps then run with more lanes, leaf steps test up to two leaves per lane; the price
 // is a stale bestT while a leaf is parked (a few more node visits).  Selected at run time (RT_EXT_SPEC).
-template <bool COUNT, bool SPEC>
+template <bool COUNT, bool SPEC, bool WIDE>
 __global__ void __launch_bounds__(kExtBlock) k_extend(const __grid_constant__ SceneView sc, PathArrays cur,
                                                       float4* __restrict__ hit, const uint32_t* __restrict__ count,
                                                       uint32_t* __restrict__ cursor, ExtendTune tune,
@@ -424,7 +455,8 @@ __global__ void __launch_bounds__(kExtBlock) k_extend(const __grid_constant__ Sc
         }
         if (node >= 0) {
             if (COUNT) visits++;
-            node_step<DEEP>(sc, r, node, sp, st);
+            if (WIDE) node_step4<DEEP>(sc, r, node, sp, st);
+            else node_step<DEEP>(sc, r, node, sp, st);
             if (SPEC) {
                 const bool park = is_leaf_code(node) & (post == kNoLeaf);
                 post = park ? node : post;
@@ -500,7 +532,7 @@ __global__ void __launch_bounds__(kExtBlock) k_extend(const __grid_constant__ Sc
         } else {
             // several node steps per vote amortise the voting overhead.  When no lane can reach the end of the
             // shared part of its stack within this round, the loop without any overflow code runs.
-            const bool deep = __any_sync(FULL, sp + tune.nodeSteps >= kShStack);
+            const bool deep = __any_sync(FULL, sp + (WIDE ? 3 : 1) * tune.nodeSteps >= kShStack);
             const float bestW = r.bestT * kWiden;
             if (!deep) {
 #pragma unroll 1
@@ -991,11 +1023,15 @@ struct Timed {
     }
 };
 
-int wf_extend_blocks_per_sm(bool instrument) {
+int wf_extend_blocks_per_sm(bool instrument, bool wide) {
     int nb = 0;
-    cudaError_t e = instrument
-        ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_extend<true, false>, kExtBlock, 0)
-        : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_extend<false, false>, kExtBlock, 0);
+    cudaError_t e;
+    if (wide)
+        e = instrument ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_extend<true, false, true>, kExtBlock, 0)
+                       : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_extend<false, true, true>, kExtBlock, 0);
+    else
+        e = instrument ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_extend<true, false, false>, kExtBlock, 0)
+                       : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_extend<false, true, false>, kExtBlock, 0);
     return e == cudaSuccess && nb > 0 ? nb : 4;
 }
 
@@ -1033,12 +1069,20 @@ cudaError_t wf_render_batch(const Launcher& L, const SceneView& sc, const WaveBu
     for (int bounce = 0; bounce < maxB; bounce++) {
         {
             Timed t(L, 0);
-            if (L.instrument)
-                k_extend<true, false><<<extGrid, kExtBlock, 0, L.st>>>(sc, a, wb.hit, wb.counts + bounce, cursors + bounce, tune, wb.stats);
+            const bool wide = sc.nodes4 != nullptr;
+            ExtendTune tw = tune;
+            tw.nodeSteps = L.node_steps_wide;
+            const int wideGrid = L.extend_grid_wide;
+            if (wide && L.instrument)
+                k_extend<true, false, true><<<wideGrid, kExtBlock, 0, L.st>>>(sc, a, wb.hit, wb.counts + bounce, cursors + bounce, tw, wb.stats);
+            else if (wide)
+                k_extend<false, true, true><<<wideGrid, kExtBlock, 0, L.st>>>(sc, a, wb.hit, wb.counts + bounce, cursors + bounce, tw, wb.stats);
+            else if (L.instrument)
+                k_extend<true, false, false><<<extGrid, kExtBlock, 0, L.st>>>(sc, a, wb.hit, wb.counts + bounce, cursors + bounce, tune, wb.stats);
             else if (L.speculative)
-                k_extend<false, true><<<extGrid, kExtBlock, 0, L.st>>>(sc, a, wb.hit, wb.counts + bounce, cursors + bounce, tune, wb.stats);
+                k_extend<false, true, false><<<extGrid, kExtBlock, 0, L.st>>>(sc, a, wb.hit, wb.counts + bounce, cursors + bounce, tune, wb.stats);
             else
-                k_extend<false, false><<<extGrid, kExtBlock, 0, L.st>>>(sc, a, wb.hit, wb.counts + bounce, cursors + bounce, tune, wb.stats);
+                k_extend<false, false, false><<<extGrid, kExtBlock, 0, L.st>>>(sc, a, wb.hit, wb.counts + bounce, cursors + bounce, tune, wb.stats);
             (*L.kernel_launches)++;
             (*L.extend_launches)++;
         }

@@ -423,6 +423,26 @@ def test_large_mesh_properties():
     assert_image_equal(a, ref, "100k-triangle frame vs oracle")
 
 
+def test_binary_and_four_wide_traversal_agree(monkeypatch, sphere_box):
+    """k_extend walks the 4-wide tree by default and the binary one with RT_BVH_WIDTH=2 (also the fallback when the
+    wide tree is too deep for the stack bound): same frame, bit for bit, and both equal to the oracle."""
+    scene, orc = sphere_box
+    cam = rt.camera_for_box(scene, 96, 64)
+    u = rt.screenshot_uniforms(scene, cam, spp=6, max_bounce=10, env_light=False)
+    ref = orc.render_frame(u, rng_mode=rt.RNG_PHILOX)
+    stats = {}
+    for width in ("2", "4"):
+        monkeypatch.setenv("RT_BVH_WIDTH", width)
+        be = backend(scene, instrument=True)
+        be.render_frame(u)
+        assert_image_equal(be.read_frame(), ref, f"RT_BVH_WIDTH={width}")
+        stats[width] = be.counters()
+        be.close()
+    assert stats["4"]["bvh_nodes"] < stats["2"]["bvh_nodes"] and stats["4"]["bvh_depth"] < stats["2"]["bvh_depth"]
+    assert stats["4"]["node_visits"] < 0.7 * stats["2"]["node_visits"]     # about half the visits
+    assert stats["4"]["segments"] == stats["2"]["segments"]
+
+
 def test_both_hierarchy_builders_give_identical_hits(monkeypatch):
     """PLOC (default) and the Karras LBVH are different trees over the same triangles; the closest-hit rule
     makes the answer independent of the hierarchy, so ids, distances and whole frames must be identical."""
