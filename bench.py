@@ -421,9 +421,10 @@ def run_gpu(args, rt):
                          "frac": (fp32_achieved / fp32_peak) if fp32_achieved else None,
                          "flops_per_segment": flops_per_seg},
                 "avg_launch_ms": avg_launch_s * 1e3, "extend_share_of_step": extend_ms / ms_total if ms_total else None,
-                "note": "algorithmic bytes = n_inner*64 + n_tri*48 + 96 per segment (SURVEY 8d); the 11 MB BVH of this "
-                        "workload is L2-resident, so achieved can exceed the HBM peak — the bound that applies is "
-                        "L2/latency, see DESIGN.md §6"}
+                "note": "algorithmic bytes = n_inner*64 + n_tri*48 + 96 per segment (SURVEY 8d; n_inner = visits of the "
+                        "64-byte 4-wide nodes k_extend walks); the 8 MB BVH of this workload is L2-resident, so this "
+                        "traffic is served on chip — the bound that applies is L2 latency / instruction issue, see "
+                        "DESIGN.md §6"}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:

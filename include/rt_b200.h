@@ -164,7 +164,7 @@ typedef struct rt_counters {
     double extend_ms;       /* device time inside k_extend (CUDA events on the ctx stream)       */
     double shade_ms;        /* device time inside raygen/shade/accumulate/resolve                */
     double build_ms;        /* device time of the last rt_scene_build                            */
-    uint64_t bvh_nodes;     /* inner nodes of the GPU BVH                                        */
+    uint64_t bvh_nodes;     /* nodes k_extend walks (4-wide)                                       */
     uint64_t bvh_bytes;     /* bytes of node + triangle arrays traversal reads                   */
     uint64_t bvh_depth;     /* longest leaf-to-root path of the GPU BVH                          */
 } rt_counters;
@@ -211,8 +211,8 @@ int rt_scene_set_texture(rt_ctx* ctx, int32_t slot, const uint8_t* pixels, int32
 
 /* Replaces `BVH BVH(bvhTriangles, rtxTriangles)` (rayTracing.cpp:1293; BVH.h:150-220) and the node
  * SSBO upload (rayTracing.cpp:1324): builds a BVH on the GPU (Morton codes, radix sort, PLOC
- * clustering — or the Karras LBVH with RT_BVH_BUILDER=lbvh — then 32-byte quantised nodes) and re-lays the
- * triangles out for traversal. */
+ * clustering — or the Karras LBVH with RT_BVH_BUILDER=lbvh — then 32-byte quantised binary nodes and their
+ * collapse into 64-byte 4-wide nodes) and re-lays the triangles out for traversal. */
 int rt_scene_build(rt_ctx* ctx);
 
 /* ---------------------------------------------------------------- render

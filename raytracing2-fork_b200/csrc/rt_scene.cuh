@@ -12,6 +12,9 @@
 //              child >= 0: inner node index; child < 0: leaf, ~child = first | (count-1) << 27.
 //              (The reference re-reads the 48-byte parent and then two 48-byte children per visit:
 //              144 B, compute.glsl:425,443-444.)
+//   nodes4   : 64 B per 4-wide node (two 256-bit loads), collapsed from the binary tree by k_collapse4: four child
+//              boxes w0..w11 (three words each, same quantisation), four children w12..w15.  k_extend walks these by
+//              default; the binary nodes serve the per-thread hooks, RT_BVH_WIDTH=2 and the deep-tree fallback.
 //   tri_geom : 64 B stride per sorted triangle; traversal reads the first 48 B = a, e0 = b-a,
 //              e1 = c-a, N = cross(e0,e1), precomputed with the very operations
 //              compute.glsl:307-309 performs per test, so every bit of dst,u,v is unchanged
