@@ -280,6 +280,12 @@ int64_t rt_split_rows(int32_t height, int32_t band_rows, int32_t rank, int32_t w
 /* Which frames does `rank` own under RT_SPLIT_FRAMES? */
 int64_t rt_split_frames(int32_t frames, int32_t rank, int32_t world_size, int32_t* frames_out,
                         int64_t cap);
+/* How rt_screenshot cuts `frames` frames of `samples_per_pixel` samples over `local_pixels` pixels into wavefront
+ * batches under a budget of `max_paths_in_flight` path slots (the loop nest that replaces the reference's
+ * per-frame dispatch, rayTracing.cpp:184-192): samples of one frame in flight together, and how many frames
+ * share a batch.  Pure host arithmetic, no GPU needed; it never changes a bit of the output. */
+int rt_plan_batches(uint64_t max_paths_in_flight, int64_t local_pixels, int32_t samples_per_pixel, int32_t frames,
+                    int32_t rng_mode, int32_t* samples_per_batch, int32_t* frames_per_batch);
 
 #ifdef __cplusplus
 }

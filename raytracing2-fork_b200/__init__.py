@@ -173,7 +173,7 @@ ABI_SYMBOLS = [
     "rt_scene_set_triangles", "rt_scene_set_materials", "rt_scene_set_texture", "rt_scene_build",
     "rt_render_frame", "rt_read_frame_rgba32f", "rt_screenshot", "rt_screenshot_device",
     "rt_screenshot_fetch", "rt_screenshot_partial", "rt_read_frame_sum", "rt_finalize_sums", "rt_first_hit", "rt_trace_rays", "rt_scene_get_bvh", "rt_get_counters",
-    "rt_reset_counters", "rt_comm_unique_id", "rt_comm_init", "rt_split_rows", "rt_split_frames",
+    "rt_reset_counters", "rt_comm_unique_id", "rt_comm_init", "rt_split_rows", "rt_split_frames", "rt_plan_batches",
 ]
 
 
@@ -510,6 +510,16 @@ def split_rows(height, band_rows, rank, world) -> np.ndarray:
     n = backend_lib().rt_split_rows(C.c_int32(height), C.c_int32(band_rows), C.c_int32(rank),
                                     C.c_int32(world), _ptr(out), C.c_int64(height))
     return out[:n]
+
+
+def plan_batches(max_paths_in_flight, local_pixels, spp, frames, rng_mode=1):
+    """(samples of a frame per batch, frames per batch) rt_screenshot will use — host arithmetic only."""
+    s, f = C.c_int32(0), C.c_int32(0)
+    rc = backend_lib().rt_plan_batches(C.c_uint64(max_paths_in_flight), C.c_int64(local_pixels), C.c_int32(spp),
+                                       C.c_int32(frames), C.c_int32(rng_mode), C.byref(s), C.byref(f))
+    if rc:
+        raise BackendError(f"rt_plan_batches failed ({rc})")
+    return s.value, f.value
 
 
 def split_frames(frames, rank, world) -> np.ndarray:

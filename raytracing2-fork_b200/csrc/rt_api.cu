@@ -327,16 +327,20 @@ uint64_t path_budget(rt_ctx* ctx) {
 }
 
 // Shape of the wavefront batches for `count` frames of `spp` samples over P local pixels:
-// samples of one frame in flight together, and how many frames share a batch.
-void batch_shape(rt_ctx* ctx, size_t P, int spp, int count, int* samples, int* frames) {
-    const uint64_t budget = path_budget(ctx);
+// samples of one frame in flight together, and how many frames share a batch (rt_plan_batches is the same
+// arithmetic exported for tests).
+void plan_batches(uint64_t budget, size_t P, int spp, int count, bool pcg, int* samples, int* frames) {
+    budget = std::min<uint64_t>(std::max<uint64_t>(budget, 1), (uint64_t)1 << 30);                    // slot ids are int32
     const uint64_t perPixel = std::max<uint64_t>(budget / std::max<size_t>(P, 1), 1);  // lanes of a pixel that fit
     // the reference stream is sequential per pixel (compute.glsl:668,683): one sample of a frame at a time
-    const uint64_t s = ctx->cfg.rng_mode == RT_RNG_REF_PCG ? 1 : std::min<uint64_t>(perPixel, (uint64_t)spp);
+    const uint64_t s = pcg ? 1 : std::min<uint64_t>(perPixel, (uint64_t)std::max(spp, 1));
     uint64_t f = 1;
-    if (s == (uint64_t)spp || ctx->cfg.rng_mode == RT_RNG_REF_PCG) f = std::max<uint64_t>(perPixel / s, 1);
+    if (s == (uint64_t)std::max(spp, 1) || pcg) f = std::max<uint64_t>(perPixel / s, 1);
     *samples = (int)s;
     *frames = (int)std::min<uint64_t>(f, (uint64_t)std::max(count, 1));
+}
+void batch_shape(rt_ctx* ctx, size_t P, int spp, int count, int* samples, int* frames) {
+    plan_batches(path_budget(ctx), P, spp, count, ctx->cfg.rng_mode == RT_RNG_REF_PCG, samples, frames);
 }
 
 int prepare_paths(rt_ctx* ctx, size_t slots, size_t frame_pixels) {
@@ -1020,6 +1024,16 @@ int64_t rt_split_frames(int32_t frames, int32_t rank, int32_t world, int32_t* fr
         n++;
     }
     return n;
+}
+
+int rt_plan_batches(uint64_t max_paths_in_flight, int64_t local_pixels, int32_t samples_per_pixel, int32_t frames,
+                    int32_t rng_mode, int32_t* samples_per_batch, int32_t* frames_per_batch) {
+    if (!samples_per_batch || !frames_per_batch || local_pixels < 0 || samples_per_pixel <= 0 || frames <= 0) return RT_ERR_INVALID;
+    int s = 1, f = 1;
+    plan_batches(max_paths_in_flight, (size_t)local_pixels, samples_per_pixel, frames, rng_mode == RT_RNG_REF_PCG, &s, &f);
+    *samples_per_batch = s;
+    *frames_per_batch = f;
+    return RT_OK;
 }
 
 }  // extern "C"

@@ -191,3 +191,30 @@ def test_two_rank_exchange_logic_on_gloo(tmp_path):
                          env=env, capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
     assert "GLOO_OK" in out.stdout
+
+
+def test_batch_planning_fills_the_budget_without_exceeding_it():
+    """rt_plan_batches = the loop nest rt_screenshot runs instead of one dispatch per frame: Philox keeps all samples
+    of a frame together when they fit and then packs whole frames; the reference stream (sequential per pixel) runs
+    one sample of as many frames as fit.  Never more slots than the budget unless one lane of the image alone
+    already exceeds it."""
+    P1080, P4k = 1920 * 1080, 3840 * 2160
+    budget = 128 << 20
+    assert rt.plan_batches(budget, P1080, 64, 4) == (64, 1)             # config 2, one GPU: a whole frame per batch
+    assert rt.plan_batches(budget, P1080 // 8, 64, 4) == (64, 4)        # an eighth of the rows (tile split, 8 GPUs)
+    assert rt.plan_batches(budget, P4k, 64, 16) == (16, 1)              # 4K: 16 samples of one frame at a time
+    assert rt.plan_batches(budget, 512 * 512, 64, 1) == (64, 1)         # config 1
+    assert rt.plan_batches(budget, 1000 * 1000, 64, 10) == (64, 2)      # the reference's default screenshot
+    assert rt.plan_batches(budget, 1000 * 1000, 64, 10, rt.RNG_REF_PCG) == (1, 10)
+    assert rt.plan_batches(budget, P1080, 64, 100, rt.RNG_REF_PCG) == (1, 64)
+    rng = np.random.default_rng(3)
+    for _ in range(300):
+        b = int(rng.integers(1, 1 << 31)); P = int(rng.integers(1, 1 << 24)); spp = int(rng.integers(1, 300))
+        frames = int(rng.integers(1, 200)); mode = int(rng.integers(0, 2))
+        s, f = rt.plan_batches(b, P, spp, frames, mode)
+        assert 1 <= s <= spp and 1 <= f <= frames
+        assert mode != rt.RNG_REF_PCG or s == 1
+        assert f == 1 or s == spp or mode == rt.RNG_REF_PCG             # frames are only packed whole
+        assert s * f * P <= max(min(b, 1 << 30), P)                     # slot ids stay below 2^30
+    with pytest.raises(rt.BackendError):
+        rt.plan_batches(budget, P1080, 0, 4)
