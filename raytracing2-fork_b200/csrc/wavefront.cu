@@ -4,7 +4,8 @@
 //
 //   k_seed_pixels   S:668       per-pixel seed of the reference's sequential stream (PCG mode)
 //   k_raygen        S:660-690   NDC of the pixel corner, defocus arc, +-1/4 pixel jitter, first ray
-//   k_extend        S:410-460   closest hit of every live path (BVH2 traversal, rt_scene.cuh)
+//   k_extend        S:410-460   closest hit of every live path: persistent warps over the 4-wide tree
+//                               (node_step4) or the binary one (node_step), slab tests in rt_scene.cuh
 //   k_shade         S:472-563   one bounce: material switch, next ray, Russian roulette; survivors
 //                               are compacted into the next queue with warp ballot + prefix popcount
 //   k_accumulate    S:692       per-pixel sum of the batch's samples, in sample order
@@ -13,8 +14,8 @@
 //   k_preview       S:565-645   traceBasic, one thread per pixel (interactive preview)
 //   k_first_hit / k_trace_rays  parity hooks
 //
-// A "path slot" is (lane, pixel): `lanes` samples of every pixel are in flight together and each
-// slot owns one float4 of `contrib`; the radiance of a path is a single value written at its
+// A "path slot" is (lane, pixel): a batch holds frames_in_batch x samples_in_batch lanes of every pixel
+// (FrameParams, rt_internal.h) and each slot owns one float4 of `contrib`; the radiance of a path is a single value written at its
 // terminal event (light hit / miss / error colour), so k_accumulate can add the lanes in sample
 // order and the image does not depend on the order in which paths finish.
 #include <type_traits>
@@ -255,7 +256,7 @@ __global__ void __launch_bounds__(kBlock) k_raygen(const __grid_constant__ Frame
 // through a device-side cursor (one atomicAdd per refill, claimed by the first idle lane), so a warp
 // never waits for its slowest ray.  Each iteration the warp VOTES on what to execute: a leaf step
 // (exact Möller–Trumbore, compute.glsl:302-340) when at least `leafVote` lanes are parked at a leaf or
-// nobody can take a node step, otherwise a node step (two slab tests) — both are executed under a
+// nobody can take a node step, otherwise a few node steps (two or four slab tests each) — both are executed under a
 // warp-uniform branch, so the instruction stream never serialises node and triangle code inside one
 // iteration.  ncu on the v1 kernel (one thread per ray, per-lane if/else) showed 6.85 of 32 lanes
 // active per instruction; this structure is what that measurement asked for
