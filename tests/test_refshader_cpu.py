@@ -157,3 +157,25 @@ def test_fuzz_oracle_equals_reference_shader(seed):
     nan_both = np.isnan(img) & np.isnan(ref)
     assert not (diff & ~nan_both).any(), f"seed {seed}: {int((diff & ~nan_both).sum())} of {diff.size} floats differ"
     assert np.unique(ref[..., :3]).size > 2   # not a blank image
+
+
+@pytest.mark.skipif(not refshader.available(True), reason="oracle/_ref/libref_shader.so not built (needs /root/reference)")
+def test_screenshot_from_reference_shader_frames():
+    """screenshot() of rayTracing.cpp:184-259 rebuilt around the reference shader: frame f is one dispatch with
+    frameIndex = f, read back as RGB8 (round to nearest), accumulated as float, divided by the frame count, clamped,
+    truncated and flipped — written here in numpy, independently of the oracle's C++ — equals orc_screenshot, which
+    the CUDA rt_screenshot is tested against."""
+    scene, u = CASES["zoo_96x64_spp8_d10_env"]
+    frames = 3
+    loaded = refshader.Loaded(scene, spec_math=True)
+    acc = np.zeros((64, 96, 3), np.float32)
+    for f in range(frames):
+        uf = u.copy(); uf["frameIndex"] = f
+        img = loaded.render(uf)[..., :3]
+        q = np.floor(np.clip(np.nan_to_num(img, nan=0.0), 0.0, 1.0) * np.float32(255.0) + np.float32(0.5)).astype(np.uint8)
+        acc += q.astype(np.float32)
+    avg = acc / np.float32(frames)
+    out = np.minimum(avg, np.float32(255.0)).astype(np.uint8)[::-1]      # truncate, then flip to top-down
+    shot, sums = oracle.OracleScene.from_scene(scene).screenshot(u, frames, rng_mode=rt.RNG_REF_PCG)
+    assert np.array_equal(shot, out)
+    assert np.array_equal(sums, acc.astype(np.uint32))
