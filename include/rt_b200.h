@@ -167,6 +167,10 @@ typedef struct rt_counters {
     uint64_t bvh_nodes;     /* nodes k_extend walks (4-wide)                                       */
     uint64_t bvh_bytes;     /* bytes of node + triangle arrays traversal reads                   */
     uint64_t bvh_depth;     /* longest leaf-to-root path of the GPU BVH                          */
+    uint64_t bvh_width;     /* 4 = k_extend walks the 4-wide nodes, 2 = the binary nodes        */
+    uint64_t bvh_stack_need;/* worst-case traversal-stack entries of that tree (must be < 256)   */
+    uint64_t bvh_build_rounds; /* clustering rounds of the last build (PLOC), 0 for the Karras tree */
+    uint64_t extend_blocks_per_sm; /* resident 128-thread blocks of the traversal kernel per SM      */
 } rt_counters;
 
 /* Host view of the GPU-built BVH, for validation only (tests check that every triangle lies in

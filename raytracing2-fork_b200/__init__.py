@@ -74,7 +74,8 @@ class Counters(C.Structure):
                 ("tri_tests", C.c_uint64), ("extend_launches", C.c_uint64),
                 ("kernel_launches", C.c_uint64), ("extend_ms", C.c_double), ("shade_ms", C.c_double),
                 ("build_ms", C.c_double), ("bvh_nodes", C.c_uint64), ("bvh_bytes", C.c_uint64),
-                ("bvh_depth", C.c_uint64)]
+                ("bvh_depth", C.c_uint64), ("bvh_width", C.c_uint64), ("bvh_stack_need", C.c_uint64),
+                ("bvh_build_rounds", C.c_uint64), ("extend_blocks_per_sm", C.c_uint64)]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}

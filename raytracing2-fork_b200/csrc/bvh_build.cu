@@ -1,7 +1,10 @@
 // bvh_build.cu — BVH construction on the GPU (replaces the reference's CPU builder,
 // RayTracing/Assets/headers/BVH.h:145-221, called at RayTracing/src/rayTracing.cpp:1293).
 //
-// Pipeline (all on the ctx stream, no host round trips apart from one 4-byte depth read-back):
+// Pipeline (all on the ctx stream).  The host reads back 8 bytes at the end of every CHUNK of clustering rounds
+// (chunks double: 4, 8, 16, ... rounds) and of every 16 collapse levels — a handful of synchronisations per build
+// instead of one per round and per level; everything else, including the cluster counts that size the work,
+// stays on the device:
 //   k_tri_bounds   per-triangle AABB + centroid, scene centroid bounds by warp shuffle + atomics
 //   k_morton       63-bit Morton code of the centroid (21 bits / axis)
 //   radix sort     hand-written stable LSD sort of (code, index): 8 passes x 8 bits, each pass
@@ -10,8 +13,10 @@
 //   hierarchy, one of
 //     PLOC (default): parallel locally-ordered clustering (Meister & Bittner 2018) over the Morton
 //                  order: every round each cluster finds the neighbour within +-kPlocRadius that
-//                  minimises the surface area of the union (k_ploc_nn), mutual pairs merge
-//                  (k_ploc_flag / k_ploc_merge), survivors are compacted by prefix scan.  An offline
+//                  minimises the surface area of the union (k_ploc_nn), mutual pairs merge and survivors are
+//                  compacted in ONE kernel (k_ploc_merge_scan: flags, single-pass decoupled-look-back prefix
+//                  scan over all tiles, merge); once <= 2048 clusters remain a single block finishes every
+//                  remaining round in shared memory (k_ploc_tail) — that is where the long chains are.  An offline
 //                  comparison (tools/bvh_quality.cpp) on the config-2 scene: 20.2 node visits per
 //                  diffuse ray against 31.0 for the Karras tree — traversal cost is what the
 //                  benchmark measures, the build stays ~2 ms.
@@ -43,7 +48,8 @@ __global__ void k_init_bounds(uint32_t* bounds) {
 
 __global__ void __launch_bounds__(256) k_tri_bounds(const rt_triangle* __restrict__ tris, int n,
                                                     float4* __restrict__ centroid,
-                                                    uint32_t* __restrict__ bounds) {
+                                                    uint32_t* __restrict__ bounds, uint32_t* __restrict__ status) {
+    bool bad = false;
     float cmin[3] = {3.4e38f, 3.4e38f, 3.4e38f}, cmax[3] = {-3.4e38f, -3.4e38f, -3.4e38f};
     float smin[3] = {3.4e38f, 3.4e38f, 3.4e38f}, smax[3] = {-3.4e38f, -3.4e38f, -3.4e38f};
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
@@ -62,7 +68,10 @@ __global__ void __launch_bounds__(256) k_tri_bounds(const rt_triangle* __restric
             smax[k] = fmaxf(smax[k], hi[k]);
         }
         centroid[i] = make_float4(ce[0], ce[1], ce[2], 0.0f);
+        // inf - inf and NaN both fail this test; such a triangle has no box to cluster by
+        bad |= !(hi[0] - lo[0] < 3.0e38f && hi[1] - lo[1] < 3.0e38f && hi[2] - lo[2] < 3.0e38f);
     }
+    if (__any_sync(0xffffffffu, bad) && (threadIdx.x & 31) == 0) atomicOr(&status[kBuildNonFinite], 1u);
 #pragma unroll
     for (int k = 0; k < 3; k++) {
 #pragma unroll
@@ -375,11 +384,22 @@ __device__ __forceinline__ float union_area(float4 alo, float4 ahi, float4 blo, 
     return dx * dy + dy * dz + dz * dx;  // symmetric in a,b bit for bit
 }
 
-// nearest neighbour in the window
-__global__ void __launch_bounds__(256) k_ploc_nn(const int32_t* __restrict__ cluster, int m, int n,
-                                                 const float4* __restrict__ boxes, int32_t* __restrict__ nn) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= m) return;
+// ---- device-side control of the clustering rounds ------------------------------------------------------------
+// ctl (uint32 words in the dead sort-histogram buffer), double buffered by round parity so that a round can read
+// its cluster count while its last tile publishes the next one:
+//   ctl[4 * (round & 1) + 0] = m        clusters entering the round
+//   ctl[4 * (round & 1) + 1] = created  inner nodes created so far
+//   ctl[8]                   = ticket   tile ids of the look-back scan are handed out in arrival order
+// tileState[t] (uint64): bits 63..62 = 0 invalid / 1 tile aggregate / 2 inclusive prefix; bits 59..32 = kept
+// clusters, bits 31..0 = merged pairs.
+constexpr int kPlocTile = 1024;        // clusters per tile of the scan (256 threads x 4)
+constexpr int kPlocTailMax = 2048;     // clusters a single block finishes on its own
+constexpr int kCtlTicket = 8;
+constexpr int kCtlWords = 16;
+constexpr unsigned long long kTileAgg = 1ull << 62, kTileIncl = 2ull << 62, kTileFlagMask = 3ull << 62;
+
+__device__ __forceinline__ int ploc_nearest(const int32_t* __restrict__ cluster, int i, int m, int n,
+                                            const float4* __restrict__ boxes) {
     const int ei = entity_of(cluster[i], n);
     const float4 lo = boxes[2 * ei], hi = boxes[2 * ei + 1];
     float best = 3.4e38f;
@@ -399,52 +419,263 @@ __global__ void __launch_bounds__(256) k_ploc_nn(const int32_t* __restrict__ clu
             bj = j;
         }
     }
-    nn[i] = bj;
+    return bj;
 }
 
-// keep[i] = 1 if position i survives the round (unmerged, or the lower half of a mutual pair);
-// merge[i] = 1 if position i creates a node
-__global__ void __launch_bounds__(256) k_ploc_flag(const int32_t* __restrict__ nn, int m, uint32_t* __restrict__ keep,
-                                                   uint32_t* __restrict__ merge) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= m) return;
-    const int j = nn[i];
-    const bool mutual = j >= 0 && nn[j] == i;
-    keep[i] = (!mutual || i < j) ? 1u : 0u;
-    merge[i] = (mutual && i < j) ? 1u : 0u;
+// one merge: node `id` = union of clusters a and b
+__device__ __forceinline__ void ploc_make_node(int id, int32_t a, int32_t b, int n, float4* __restrict__ boxes,
+                                               int32_t* __restrict__ children, uint32_t* __restrict__ height,
+                                               int32_t* __restrict__ parentOf, uint32_t* __restrict__ innerCount) {
+    const int ea = entity_of(a, n), eb = entity_of(b, n);
+    const float4 alo = boxes[2 * ea], ahi = boxes[2 * ea + 1], blo = boxes[2 * eb], bhi = boxes[2 * eb + 1];
+    boxes[2 * id] = make_float4(fminf(alo.x, blo.x), fminf(alo.y, blo.y), fminf(alo.z, blo.z), 0.0f);
+    boxes[2 * id + 1] = make_float4(fmaxf(ahi.x, bhi.x), fmaxf(ahi.y, bhi.y), fmaxf(ahi.z, bhi.z), 0.0f);
+    children[2 * id] = a;
+    children[2 * id + 1] = b;
+    height[id] = max(height[ea], height[eb]) + 1u;
+    // bookkeeping for the depth-first relabelling: parent links and inner nodes per subtree
+    if (a >= 0) parentOf[a] = id;
+    if (b >= 0) parentOf[b] = id;
+    innerCount[id] = 1u + (a >= 0 ? innerCount[a] : 0u) + (b >= 0 ? innerCount[b] : 0u);
 }
 
-// keepPos / mergePos hold the exclusive scans of the flags.  Node ids are handed out from the top so
-// that the last node created (the root) is node 0 and the upper levels are contiguous in memory.
-__global__ void __launch_bounds__(256) k_ploc_merge(const int32_t* __restrict__ clusterIn, const int32_t* __restrict__ nn,
-                                                    int m, int n, const uint32_t* __restrict__ keepPos,
-                                                    const uint32_t* __restrict__ mergePos, int firstId,
-                                                    float4* __restrict__ boxes, int32_t* __restrict__ children,
-                                                    uint32_t* __restrict__ height, int32_t* __restrict__ parentOf,
-                                                    uint32_t* __restrict__ innerCount, int32_t* __restrict__ clusterOut) {
+__global__ void k_ploc_ctl_init(uint32_t* __restrict__ ctl, int n) {
+    if (threadIdx.x < kCtlWords) ctl[threadIdx.x] = 0u;
+    __syncwarp();
+    if (threadIdx.x == 0) ctl[0] = (uint32_t)n;
+}
+
+// nearest neighbour in the window; also re-arms the scan of this round (ticket, tile states)
+__global__ void __launch_bounds__(256) k_ploc_nn(int n, int round, uint32_t* __restrict__ ctl,
+                                                 unsigned long long* __restrict__ tileState,
+                                                 const int32_t* __restrict__ cluster,
+                                                 const float4* __restrict__ boxes, int32_t* __restrict__ nn) {
+    const uint32_t* cin = ctl + 4 * (round & 1);
+    uint32_t* cout = ctl + 4 * ((round + 1) & 1);
+    const int m = (int)cin[0];
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= m) return;
-    const int j = nn[i];
-    const bool mutual = j >= 0 && nn[j] == i;
-    if (mutual && i > j) return;
-    int32_t c = clusterIn[i];
-    if (mutual) {
-        const int32_t a = c, b = clusterIn[j];
-        const int id = firstId - (int)mergePos[i];
-        const int ea = entity_of(a, n), eb = entity_of(b, n);
-        const float4 alo = boxes[2 * ea], ahi = boxes[2 * ea + 1], blo = boxes[2 * eb], bhi = boxes[2 * eb + 1];
-        boxes[2 * id] = make_float4(fminf(alo.x, blo.x), fminf(alo.y, blo.y), fminf(alo.z, blo.z), 0.0f);
-        boxes[2 * id + 1] = make_float4(fmaxf(ahi.x, bhi.x), fmaxf(ahi.y, bhi.y), fmaxf(ahi.z, bhi.z), 0.0f);
-        children[2 * id] = a;
-        children[2 * id + 1] = b;
-        height[id] = max(height[ea], height[eb]) + 1u;
-        // bookkeeping for the depth-first relabelling: parent links and inner nodes per subtree
-        if (a >= 0) parentOf[a] = id;
-        if (b >= 0) parentOf[b] = id;
-        innerCount[id] = 1u + (a >= 0 ? innerCount[a] : 0u) + (b >= 0 ? innerCount[b] : 0u);
-        c = id;
+    if (i == 0) {
+        ctl[kCtlTicket] = 0u;
+        if (m <= kPlocTailMax) {  // nothing (more) to do globally: the round is a no-op, the state moves on unchanged
+            cout[0] = cin[0];
+            cout[1] = cin[1];
+        }
     }
-    clusterOut[keepPos[i]] = c;
+    if (m <= kPlocTailMax) return;
+    if (i < (m + kPlocTile - 1) / kPlocTile) tileState[i] = 0ull;
+    if (i >= m) return;
+    nn[i] = ploc_nearest(cluster, i, m, n, boxes);
+}
+
+// Flags (mutual pair -> the lower position creates a node, the upper one disappears), exclusive prefix sums of
+// "kept" and "merged" over ALL clusters in a single pass (decoupled look-back over the tiles, Merrill & Garland),
+// and the merge itself.  The last tile publishes the next round's cluster count.
+__global__ void __launch_bounds__(256) k_ploc_merge_scan(int n, int round, uint32_t* __restrict__ ctl,
+                                                         unsigned long long* __restrict__ tileState,
+                                                         const int32_t* __restrict__ clusterIn,
+                                                         int32_t* __restrict__ clusterOut,
+                                                         const int32_t* __restrict__ nn, float4* __restrict__ boxes,
+                                                         int32_t* __restrict__ children, uint32_t* __restrict__ height,
+                                                         int32_t* __restrict__ parentOf,
+                                                         uint32_t* __restrict__ innerCount,
+                                                         uint32_t* __restrict__ status) {
+    const uint32_t* cin = ctl + 4 * (round & 1);
+    uint32_t* cout = ctl + 4 * ((round + 1) & 1);
+    const int m = (int)cin[0];
+    const int created = (int)cin[1];
+    if (m <= kPlocTailMax) return;
+    __shared__ uint32_t sTile;
+    __shared__ unsigned long long sWarp[8];
+    __shared__ unsigned long long sPrefix;
+    if (threadIdx.x == 0) sTile = atomicAdd(&ctl[kCtlTicket], 1u);
+    __syncthreads();
+    const int tile = (int)sTile;
+    const int tiles = (m + kPlocTile - 1) / kPlocTile;
+    if (tile >= tiles) return;
+
+    const int base = tile * kPlocTile + threadIdx.x * 4;
+    int32_t c[4];
+    int j[4];
+    bool mutual[4];
+    unsigned long long mine = 0ull;  // kept << 32 | merged
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const int i = base + k;
+        j[k] = -1;
+        mutual[k] = false;
+        c[k] = 0;
+        if (i < m) {
+            j[k] = nn[i];
+            mutual[k] = j[k] >= 0 && nn[j[k]] == i;
+            c[k] = clusterIn[i];
+            const bool keep = !mutual[k] || i < j[k];
+            const bool merge = mutual[k] && i < j[k];
+            mine += ((unsigned long long)(keep ? 1u : 0u) << 32) | (unsigned long long)(merge ? 1u : 0u);
+        }
+    }
+    // block-wide inclusive scan of the per-thread sums
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned long long incl = mine;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        const unsigned long long t = __shfl_up_sync(0xffffffffu, incl, off);
+        if (lane >= off) incl += t;
+    }
+    if (lane == 31) sWarp[warp] = incl;
+    __syncthreads();
+    unsigned long long warpBase = 0ull, tileTotal = 0ull;
+#pragma unroll
+    for (int w = 0; w < 8; w++) {
+        if (w < warp) warpBase += sWarp[w];
+        tileTotal += sWarp[w];
+    }
+    // look-back: thread 0 publishes the tile aggregate, then sums its predecessors until one holds an inclusive prefix
+    if (threadIdx.x == 0) {
+        volatile unsigned long long* ts = tileState;
+        unsigned long long prefix = 0ull;
+        if (tile == 0) {
+            ts[0] = kTileIncl | tileTotal;
+        } else {
+            ts[tile] = kTileAgg | tileTotal;
+            __threadfence();
+            for (int t = tile - 1; t >= 0; t--) {
+                unsigned long long v;
+                do { v = ts[t]; } while ((v & kTileFlagMask) == 0ull);
+                prefix += v & ~kTileFlagMask;
+                if ((v & kTileFlagMask) == kTileIncl) break;
+            }
+            ts[tile] = kTileIncl | (prefix + tileTotal);
+        }
+        __threadfence();
+        sPrefix = prefix;
+        if (tile == tiles - 1) {  // grand totals: the state of the next round
+            const unsigned long long total = prefix + tileTotal;
+            const uint32_t kept = (uint32_t)(total >> 32), merged = (uint32_t)(total & 0xffffffffu);
+            if (merged == 0u) {  // no mutual pair (union areas overflowed): give up, the caller builds a Karras tree
+                status[kBuildPlocStuck] = 1u;
+                cout[0] = 0u;
+            } else {
+                cout[0] = kept;
+            }
+            cout[1] = (uint32_t)created + merged;
+            status[kBuildPlocRounds] = (uint32_t)round + 1u;
+        }
+    }
+    __syncthreads();
+    unsigned long long run = sPrefix + warpBase + incl - mine;  // exclusive prefix of this thread's first item
+    const int firstId = (n - 2) - created;  // node ids are handed out from the top: the last node created (the root) is 0
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const int i = base + k;
+        if (i >= m) break;
+        const bool upper = mutual[k] && i > j[k];
+        if (!upper) {
+            int32_t out = c[k];
+            if (mutual[k]) {
+                const int id = firstId - (int)(uint32_t)(run & 0xffffffffu);
+                ploc_make_node(id, c[k], clusterIn[j[k]], n, boxes, children, height, parentOf, innerCount);
+                out = id;
+                run += 1ull;
+            }
+            clusterOut[(uint32_t)(run >> 32)] = out;
+            run += 1ull << 32;
+        }
+    }
+}
+
+// The last <= kPlocTailMax clusters: one block runs every remaining round (nearest neighbour, flags, scan, merge)
+// with the cluster list in shared memory.  Most ROUNDS of a build happen here — the cluster count falls
+// geometrically at first and then the large clusters absorb the stragglers one or two per round.
+__global__ void __launch_bounds__(1024) k_ploc_tail(int n, int round, uint32_t* __restrict__ ctl,
+                                                    const int32_t* __restrict__ clusterIn, float4* __restrict__ boxes,
+                                                    int32_t* __restrict__ children, uint32_t* __restrict__ height,
+                                                    int32_t* __restrict__ parentOf, uint32_t* __restrict__ innerCount,
+                                                    uint32_t* __restrict__ status) {
+    uint32_t* cio = ctl + 4 * (round & 1);
+    int m = (int)cio[0];
+    int created = (int)cio[1];
+    if (m <= 1 || m > kPlocTailMax) return;
+    __shared__ int32_t cl[2][kPlocTailMax];
+    __shared__ int32_t snn[kPlocTailMax];
+    __shared__ uint32_t sWarp[32];
+    __shared__ uint32_t sTotal;
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    for (int i = t; i < m; i += 1024) cl[0][i] = clusterIn[i];
+    __syncthreads();
+    int cur = 0;
+    uint32_t rounds = (uint32_t)round;
+    bool stuck = false;
+    while (m > 1) {
+        for (int i = t; i < m; i += 1024) snn[i] = ploc_nearest(cl[cur], i, m, n, boxes);
+        __syncthreads();
+        // items 2t, 2t+1; packed sums: kept << 16 | merged (both <= 2048)
+        uint32_t mine = 0u;
+        bool mutual[2];
+        int j[2];
+#pragma unroll
+        for (int k = 0; k < 2; k++) {
+            const int i = 2 * t + k;
+            j[k] = -1;
+            mutual[k] = false;
+            if (i < m) {
+                j[k] = snn[i];
+                mutual[k] = j[k] >= 0 && snn[j[k]] == i;
+                mine += ((!mutual[k] || i < j[k]) ? (1u << 16) : 0u) | ((mutual[k] && i < j[k]) ? 1u : 0u);
+            }
+        }
+        uint32_t incl = mine;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            const uint32_t v = __shfl_up_sync(0xffffffffu, incl, off);
+            if (lane >= off) incl += v;
+        }
+        if (lane == 31) sWarp[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            uint32_t w = sWarp[lane];
+#pragma unroll
+            for (int off = 1; off < 32; off <<= 1) {
+                const uint32_t v = __shfl_up_sync(0xffffffffu, w, off);
+                if (lane >= off) w += v;
+            }
+            sWarp[lane] = w;  // inclusive over warps
+            if (lane == 31) sTotal = w;
+        }
+        __syncthreads();
+        uint32_t run = (warp ? sWarp[warp - 1] : 0u) + incl - mine;
+        const uint32_t total = sTotal;
+        const int firstId = (n - 2) - created;
+#pragma unroll
+        for (int k = 0; k < 2; k++) {
+            const int i = 2 * t + k;
+            if (i >= m) break;
+            const bool upper = mutual[k] && i > j[k];
+            if (!upper) {
+                int32_t out = cl[cur][i];
+                if (mutual[k]) {
+                    const int id = firstId - (int)(run & 0xffffu);
+                    ploc_make_node(id, out, cl[cur][j[k]], n, boxes, children, height, parentOf, innerCount);
+                    out = id;
+                    run += 1u;
+                }
+                cl[cur ^ 1][run >> 16] = out;
+                run += 1u << 16;
+            }
+        }
+        rounds++;
+        const uint32_t merged = total & 0xffffu;
+        if (merged == 0u) { stuck = true; break; }
+        created += (int)merged;
+        m = (int)(total >> 16);
+        cur ^= 1;
+        __syncthreads();  // node boxes / heights written above are read by everybody in the next round
+    }
+    if (t == 0) {
+        cio[0] = stuck ? 0u : 1u;
+        cio[1] = (uint32_t)created;
+        status[kBuildPlocRounds] = rounds;
+        if (stuck) status[kBuildPlocStuck] = 1u;
+    }
 }
 
 // Depth-first (pre-order) position of every inner node: walk up to the root adding 1 per level and
@@ -530,16 +761,27 @@ __global__ void __launch_bounds__(256) k_emit_nodes(int n, const int32_t* __rest
 // 64 bytes per node = 4 x (3 words of lo | hi << 16) + 4 children.
 // Numbering depends on atomics (topology does not), which is harmless: the closest-hit rule makes the image
 // independent of the hierarchy's layout.
-__global__ void __launch_bounds__(256) k_collapse4(int n, const int32_t* __restrict__ children,
+// Counters (uint32, in the dead histogram buffer): cnt[0..2] = queue sizes, rotating (level L reads cnt[L % 3],
+// appends to cnt[(L + 1) % 3] and clears cnt[(L + 2) % 3] for the level after next), cnt[3] = levels that had work.
+// wide[0] = wide nodes allocated, wide[1] = worst-case number of traversal-stack entries: a visit of a node with k
+// children pushes at most k - 1 of them, so the deepest stack any ray can build is the largest sum of (k - 1)
+// along a root-to-leaf path; needOf[wide index] carries that sum down the levels.
+__global__ void __launch_bounds__(256) k_collapse4(int n, int level, const int32_t* __restrict__ children,
                                                    const float4* __restrict__ boxes, const float* __restrict__ grid,
-                                                   const int2* __restrict__ qin, const uint32_t* __restrict__ qinCount,
-                                                   int2* __restrict__ qout, uint32_t* __restrict__ qoutCount,
-                                                   uint32_t* __restrict__ wideCount, uint4* __restrict__ nodes4) {
+                                                   const int2* __restrict__ qin, int2* __restrict__ qout,
+                                                   uint32_t* __restrict__ cnt, uint32_t* __restrict__ wide,
+                                                   uint32_t* __restrict__ needOf, uint4* __restrict__ nodes4) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= *qinCount) return;
+    const uint32_t count = cnt[level % 3];
+    uint32_t* qoutCount = cnt + (level + 1) % 3;
+    if (i == 0) {
+        cnt[(level + 2) % 3] = 0u;
+        if (count > 0u) cnt[3] = (uint32_t)level + 1u;
+    }
+    if (i >= count) return;
     const int2 e = qin[i];
     int32_t slot[4] = {children[2 * e.x], children[2 * e.x + 1], -1, -1};
-    int cnt = 2;
+    int cnt4 = 2;
     auto ent = [&](int32_t c) { return c >= 0 ? c : (n - 1 + ~c); };
     auto area = [&](int32_t c) {
         const float4 lo = boxes[2 * ent(c)], hi = boxes[2 * ent(c) + 1];
@@ -549,7 +791,7 @@ __global__ void __launch_bounds__(256) k_collapse4(int n, const int32_t* __restr
     for (int round = 0; round < 2; round++) {
         int best = -1;
         float bestA = -1.0f;
-        for (int k = 0; k < cnt; k++)
+        for (int k = 0; k < cnt4; k++)
             if (slot[k] >= 0) {
                 const float a = area(slot[k]);
                 if (a > bestA) { bestA = a; best = k; }
@@ -557,8 +799,10 @@ __global__ void __launch_bounds__(256) k_collapse4(int n, const int32_t* __restr
         if (best < 0) break;
         const int32_t open = slot[best];
         slot[best] = children[2 * open];
-        slot[cnt++] = children[2 * open + 1];
+        slot[cnt4++] = children[2 * open + 1];
     }
+    const uint32_t need = needOf[e.y] + (uint32_t)(cnt4 - 1);
+    atomicMax(&wide[1], need);
     auto qlo = [&](float v, int k) {
         const float c = floorf((v - grid[k]) * grid[3 + k] - kGuardCells);
         return (uint32_t)fminf(fmaxf(c, 0.0f), 65535.0f);
@@ -569,14 +813,15 @@ __global__ void __launch_bounds__(256) k_collapse4(int n, const int32_t* __restr
     };
     uint32_t w[16];
     for (int k = 0; k < 4; k++) {
-        if (k < cnt) {
+        if (k < cnt4) {
             const float4 lo = boxes[2 * ent(slot[k])], hi = boxes[2 * ent(slot[k]) + 1];
             w[3 * k + 0] = qlo(lo.x, 0) | (qhi(hi.x, 0) << 16);
             w[3 * k + 1] = qlo(lo.y, 1) | (qhi(hi.y, 1) << 16);
             w[3 * k + 2] = qlo(lo.z, 2) | (qhi(hi.z, 2) << 16);
             int32_t ref;
             if (slot[k] >= 0) {
-                ref = (int32_t)atomicAdd(wideCount, 1u);
+                ref = (int32_t)atomicAdd(&wide[0], 1u);
+                needOf[ref] = need;
                 qout[atomicAdd(qoutCount, 1u)] = make_int2(slot[k], ref);
             } else {
                 ref = pack_leaf(~slot[k], 1);
@@ -593,13 +838,20 @@ __global__ void __launch_bounds__(256) k_collapse4(int n, const int32_t* __restr
     dst[2] = make_uint4(w[8], w[9], w[10], w[11]);
     dst[3] = make_uint4(w[12], w[13], w[14], w[15]);
 }
-__global__ void k_collapse_init(int2* q, uint32_t* counters) {
+__global__ void k_collapse_init(int2* q, uint32_t* cnt, uint32_t* wide, uint32_t* needOf) {
     if (threadIdx.x == 0) {
         q[0] = make_int2(0, 0);  // the binary root becomes wide node 0
-        counters[0] = 1u;        // wide nodes allocated
-        counters[1] = 1u;        // entries in queue A
-        counters[2] = 0u;        // entries in queue B
+        cnt[0] = 1u;             // entries in the level-0 queue
+        cnt[1] = 0u;
+        cnt[2] = 0u;
+        cnt[3] = 0u;             // levels
+        wide[0] = 1u;            // wide nodes allocated
+        wide[1] = 0u;            // worst-case stack entries
+        needOf[0] = 0u;
     }
+}
+__global__ void k_set_word(uint32_t* p, uint32_t v) {
+    if (threadIdx.x == 0) *p = v;
 }
 
 // Sorted triangle records.  e0, e1 and N are computed with exactly the operations of
@@ -631,14 +883,15 @@ __global__ void k_iota(uint32_t* v, int n) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// Host driver.  Returns the tree depth through *depthOut (one small D2H after the build).
+// Host driver.  Depth, error flags and the wide-tree counters stay on the device for rt_scene_build to read.
 cudaError_t build_lbvh(const BuildArgs& a, cudaStream_t st, uint64_t* launches) {
     const int n = a.n;
-    auto nb = [](int count, int per) { return (count + per - 1) / per; };
+    auto nb = [](long long count, int per) { return (int)((count + per - 1) / per); };
     uint64_t L = 0;
+    uint32_t* maxDepth = a.status + kBuildDepth;
+    cudaMemsetAsync(a.status, 0, kBuildStatusWords * sizeof(uint32_t), st);
     k_init_bounds<<<1, 32, 0, st>>>(a.bounds); L++;
-    k_tri_bounds<<<min(nb(n, 256), 148 * 8), 256, 0, st>>>(a.tris, n, a.centroid, a.bounds); L++;
-    cudaMemsetAsync(a.maxDepth, 0, sizeof(uint32_t), st);
+    k_tri_bounds<<<min(nb(n, 256), a.sm_count * 8), 256, 0, st>>>(a.tris, n, a.centroid, a.bounds, a.status); L++;
     if (n >= 2) {
         k_morton<<<nb(n, 256), 256, 0, st>>>(a.centroid, n, a.bounds, a.keys[0], a.vals[0]); L++;
         const int nblocks = nb(n, kSortTile);
@@ -660,31 +913,42 @@ cudaError_t build_lbvh(const BuildArgs& a, cudaStream_t st, uint64_t* launches) 
         // scratch: the sort's second key/value buffers are free now
         int32_t* cluster[2] = {reinterpret_cast<int32_t*>(a.vals[1]), a.parent};
         int32_t* nn = a.parent + n;                      // parent has 2n entries
-        uint32_t* keep = a.flags;                         // n + 1 entries each (scan total in the last slot)
-        uint32_t* merge = reinterpret_cast<uint32_t*>(a.keys[1]);
         uint32_t* height = a.nodeDepth;                   // 2n - 1 entries
         int32_t* parentOf = reinterpret_cast<int32_t*>(a.centroid);     // centroids are dead after k_morton: 16n bytes
         uint32_t* innerCount = reinterpret_cast<uint32_t*>(a.centroid) + n;
+        uint32_t* ctl = a.hist;                           // the histograms are dead after the sort
+        unsigned long long* tileState = reinterpret_cast<unsigned long long*>(a.hist + kCtlWords);
         k_ploc_init<<<nb(n, 256), 256, 0, st>>>(a.tris, a.vals[0], n, a.bounds, a.boxes, cluster[0], height); L++;
-        int m = n, created = 0, cur = 0;
-        uint32_t totals[2];
-        while (m > 1) {
-            k_ploc_nn<<<nb(m, 256), 256, 0, st>>>(cluster[cur], m, n, a.boxes, nn); L++;
-            k_ploc_flag<<<nb(m, 256), 256, 0, st>>>(nn, m, keep, merge); L++;
-            k_scan<<<1, 1024, 0, st>>>(keep, m); L++;
-            k_scan<<<1, 1024, 0, st>>>(merge, m); L++;
-            k_ploc_merge<<<nb(m, 256), 256, 0, st>>>(cluster[cur], nn, m, n, keep, merge, (n - 2) - created, a.boxes,
-                                                     a.children, height, parentOf, innerCount, cluster[cur ^ 1]); L++;
-            cudaMemcpyAsync(&totals[0], keep + m, sizeof(uint32_t), cudaMemcpyDeviceToHost, st);
-            cudaMemcpyAsync(&totals[1], merge + m, sizeof(uint32_t), cudaMemcpyDeviceToHost, st);
+        k_ploc_ctl_init<<<1, 32, 0, st>>>(ctl, n); L++;
+        // Rounds are enqueued in chunks without the host knowing the cluster count (kernels read it from `ctl`;
+        // grids are sized for the count at the start of the chunk, surplus blocks exit at once); after each chunk
+        // the single-block tail gets a chance and the host reads back two words.
+        int round = 0, chunk = 4;
+        uint32_t m = (uint32_t)n;
+        const int kMaxGlobalRounds = 1024;
+        while (m > 1u) {
+            if (m > (uint32_t)kPlocTailMax) {
+                for (int k = 0; k < chunk; k++, round++) {
+                    k_ploc_nn<<<nb(m, 256), 256, 0, st>>>(n, round, ctl, tileState, cluster[round & 1], a.boxes, nn); L++;
+                    k_ploc_merge_scan<<<nb(m, kPlocTile), 256, 0, st>>>(n, round, ctl, tileState, cluster[round & 1],
+                                                                         cluster[(round + 1) & 1], nn, a.boxes, a.children,
+                                                                         height, parentOf, innerCount, a.status); L++;
+                }
+                chunk = min(chunk * 2, 64);
+            }
+            k_ploc_tail<<<1, 1024, 0, st>>>(n, round, ctl, cluster[round & 1], a.boxes, a.children, height, parentOf,
+                                            innerCount, a.status); L++;
+            uint32_t state[2];
+            cudaMemcpyAsync(state, ctl + 4 * (round & 1), sizeof state, cudaMemcpyDeviceToHost, st);
             cudaError_t e = cudaStreamSynchronize(st);
             if (e != cudaSuccess) return e;
-            if (totals[1] == 0u || (int)totals[0] >= m) return cudaErrorUnknown;  // cannot happen: a mutual pair always exists
-            created += (int)totals[1];
-            m = (int)totals[0];
-            cur ^= 1;
+            m = state[0];
+            if (m > 1u && round >= kMaxGlobalRounds) {  // runs of identical boxes merge one pair per round: not worth waiting for
+                k_set_word<<<1, 32, 0, st>>>(a.status + kBuildPlocStuck, 1u); L++;
+                m = 0u;
+            }
         }
-        k_ploc_depth<<<1, 32, 0, st>>>(height, a.maxDepth); L++;
+        k_ploc_depth<<<1, 32, 0, st>>>(height, maxDepth); L++;
         if (a.dfs_layout) {
             order = reinterpret_cast<int32_t*>(a.centroid) + 2 * (size_t)n;
             k_dfs_order<<<nb(n - 1, 256), 256, 0, st>>>(n, a.children, parentOf, innerCount, order); L++;
@@ -696,35 +960,49 @@ cudaError_t build_lbvh(const BuildArgs& a, cudaStream_t st, uint64_t* launches) 
             cudaMemsetAsync(a.nodeDepth, 0, sizeof(uint32_t) * (size_t)(n - 1), st);
         }
         k_refit<<<nb(n, 256), 256, 0, st>>>(a.tris, a.vals[0], n, a.bounds, a.children, a.parent, a.boxes, a.flags,
-                                            a.nodeDepth, a.maxDepth); L++;
+                                            a.nodeDepth, maxDepth); L++;
     }
     k_grid<<<1, 32, 0, st>>>(a.bounds, a.grid); L++;
     if (n >= 2) { k_emit_nodes<<<nb(n - 1, 256), 256, 0, st>>>(n, a.children, a.boxes, a.grid, order, a.nodes); L++; }
     if (n >= 2 && a.nodes4) {
-        // queues in the two key buffers of the sort (n int2 each, dead by now); counters in the histogram buffer
+        // queues in the two key buffers of the sort (n int2 each, dead by now); counters behind the PLOC control
+        // block; per-node stack need in the height array (dead after k_ploc_depth / k_refit)
         int2* q[2] = {reinterpret_cast<int2*>(a.keys[0]), reinterpret_cast<int2*>(a.keys[1])};
-        uint32_t* counters = a.hist;  // [0] wide nodes, [1] |queue A|, [2] |queue B|
-        k_collapse_init<<<1, 32, 0, st>>>(q[0], counters); L++;
-        uint32_t level = 1;
-        int cur = 0, levels = 0;
-        while (level > 0) {
-            levels++;
-            k_collapse4<<<nb((int)level, 256), 256, 0, st>>>(n, a.children, a.boxes, a.grid, q[cur], counters + 1 + cur,
-                                                             q[cur ^ 1], counters + 1 + (cur ^ 1), counters, a.nodes4); L++;
-            cudaMemsetAsync(counters + 1 + cur, 0, sizeof(uint32_t), st);  // this queue is the next level's output
-            cudaMemcpyAsync(&level, counters + 1 + (cur ^ 1), sizeof(uint32_t), cudaMemcpyDeviceToHost, st);
+        uint32_t* cnt = a.hist + 32;
+        uint32_t* needOf = a.nodeDepth;
+        k_collapse_init<<<1, 32, 0, st>>>(q[0], cnt, a.wide_count, needOf); L++;
+        // levels are enqueued 16 at a time with grids sized by the bound min(4^level, n - 1) on the queue length;
+        // an empty level is a no-op, and after each group the host reads one word to see whether work remains
+        int level = 0;
+        uint32_t pending = 1u;
+        while (pending > 0u) {
+            for (int k = 0; k < 16; k++, level++) {
+                const long long bound = level < 13 ? (1ll << (2 * level)) : (long long)n;
+                const long long cap = bound < (long long)(n - 1) ? bound : (long long)(n - 1);
+                k_collapse4<<<nb(cap, 256), 256, 0, st>>>(n, level, a.children, a.boxes, a.grid, q[level & 1],
+                                                          q[(level + 1) & 1], cnt, a.wide_count, needOf, a.nodes4); L++;
+            }
+            cudaMemcpyAsync(&pending, cnt + level % 3, sizeof(uint32_t), cudaMemcpyDeviceToHost, st);
             cudaError_t e = cudaStreamSynchronize(st);
             if (e != cudaSuccess) return e;
-            cur ^= 1;
         }
-        cudaMemcpyAsync(a.wide_count, counters, sizeof(uint32_t), cudaMemcpyDeviceToDevice, st);
-        if (a.wide_levels) *a.wide_levels = levels;
+        uint32_t levels = 0;
+        cudaMemcpyAsync(&levels, cnt + 3, sizeof(uint32_t), cudaMemcpyDeviceToHost, st);
+        cudaError_t e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess) return e;
+        if (a.wide_levels) *a.wide_levels = (int)levels;
     }
     k_emit_tris<<<nb(n, 256), 256, 0, st>>>(a.tris, a.vals[0], n, a.geom, a.shade, a.orig); L++;
     if (launches) *launches += L;
     return cudaGetLastError();
 }
 
-size_t sort_hist_entries(int n) { return (size_t)256 * ((n + kSortTile - 1) / kSortTile) + 1; }  // +1: k_scan stores the total
+// sort histograms (+1: k_scan stores the total); the same words later hold the PLOC control block, the tile
+// states of its scan (one uint64 per kPlocTile clusters) and the collapse counters
+size_t build_scratch_words(int n) {
+    const size_t sortWords = (size_t)256 * ((n + kSortTile - 1) / kSortTile) + 1;
+    const size_t plocWords = (size_t)kCtlWords + 2 * ((size_t)(n + kPlocTile - 1) / kPlocTile + 1) + 64;
+    return sortWords > plocWords ? sortWords : plocWords;
+}
 
 }  // namespace rt

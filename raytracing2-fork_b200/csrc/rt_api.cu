@@ -6,6 +6,7 @@
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
+#include <cmath>
 #include <cstring>
 #include <new>
 #include <string>
@@ -39,11 +40,8 @@ struct NcclApi {
     bool ok = false;
     std::string err;
 };
-NcclApi& nccl() {
-    static NcclApi api;
-    static bool tried = false;
-    if (tried) return api;
-    tried = true;
+NcclApi load_nccl() {
+    NcclApi api;
     const char* names[] = {"libnccl.so.2", "libnccl.so"};
     for (const char* n : names) {
         api.handle = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
@@ -68,11 +66,20 @@ NcclApi& nccl() {
     if (!api.ok) api.err = "libnccl.so.2 lacks a required symbol";
     return api;
 }
+// function-local static: initialised exactly once, also when two threads create contexts concurrently
+NcclApi& nccl() {
+    static NcclApi api = load_nccl();
+    return api;
+}
 
 // ---------------------------------------------------------------------------------------------- device buffers
 struct DevBuf {
     void* p = nullptr;
     size_t cap = 0;
+    DevBuf() = default;
+    DevBuf(const DevBuf&) = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+    ~DevBuf() { release(); }  // every buffer a ctx owns goes with it: nothing to list in rt_destroy
     cudaError_t reserve(size_t bytes) {
         if (bytes <= cap) return cudaSuccess;
         if (p) cudaFree(p);
@@ -105,9 +112,15 @@ struct rt_ctx {
     int leaf_vote = 12, refill = 8, node_steps = 4;
     int node_steps_wide = 2, extend_blocks_per_sm_wide = 8;
     int use_ploc = 1, dfs_layout = 1, speculative = 1, shade_blocks_per_sm = 64;
+    int top_smem = 0;              // RT_EXT_TOP=1: k_extend keeps the top four levels of the wide tree in shared memory
+    int shade_bin = 1, shade_oct = 1;  // k_shade: block-local material queues / octant-ordered block output
+    int hooks_thread = 0;          // RT_HOOKS=thread: parity hooks walk the binary tree per thread (preview's code path)
+    int extend_blocks_per_sm_top = 8;
     int bvh_width = 4;             // 4: k_extend walks 4-wide nodes collapsed from the binary tree; 2: the binary tree (RT_BVH_WIDTH)
-    DevBuf d_nodes4, d_wide_count;
+    DevBuf d_wide_count;           // [0] wide nodes written, [1] worst-case traversal stack entries (k_collapse4)
     uint32_t wide_nodes = 0;
+    uint32_t wide_stack_need = 0;
+    uint32_t build_rounds = 0;
     int wide_depth = 0;
     bool wide_ok = false;          // 4-wide nodes built and the stack bound (3 pushes per level) holds
     int l2_max_persist = -1, l2_max_window = 0;  // device limits, -1 = not queried yet
@@ -130,18 +143,21 @@ struct rt_ctx {
     int tex_w[RT_MAX_TEXTURES] = {0}, tex_h[RT_MAX_TEXTURES] = {0}, tex_ch[RT_MAX_TEXTURES] = {0};
     // build scratch + outputs
     DevBuf d_centroid, d_bounds, d_keys[2], d_vals[2], d_hist, d_children, d_parent, d_boxes, d_flags, d_depth, d_node_depth;
-    DevBuf d_bvh, d_grid;  // d_bvh = one arena: nodes | tri_geom | tri_orig | tri_shade (one L2 persisting window)
+    DevBuf d_bvh, d_grid;  // d_bvh = one arena: nodes | nodes4 | tri_geom | tri_orig | tri_shade (one L2 persisting window)
     uint4* p_nodes = nullptr;
+    uint4* p_nodes4 = nullptr;   // inside the arena, right in front of the triangle records
+    const void* hot_base = nullptr;  // what k_extend gathers from: [nodes4 or nodes, tri_orig end)
+    cudaEvent_t build_ev[2] = {nullptr, nullptr};
     float4* p_geom = nullptr;
     float4* p_shade = nullptr;
     int32_t* p_orig = nullptr;
-    size_t bvh_hot_bytes = 0;  // nodes + tri_geom + tri_orig: what k_extend gathers from
+    size_t bvh_hot_bytes = 0;  // (wide or binary) nodes + tri_geom + tri_orig
     int l2_persist = 1;
     float grid[6] = {0, 0, 0, 1, 1, 1};
     // wavefront
     DevBuf d_path[6], d_hit, d_contrib, d_accum, d_pixrng, d_counts, d_stats, d_image, d_sum, d_out, d_rows;
     DevBuf d_stage, d_compact;  // tile-split gather
-    DevBuf d_scratch[6];        // first-hit / trace-rays staging
+    DevBuf d_scratch[10];       // first-hit / trace-rays staging: in, out, ray queue, hits, counts
     int width = 0, height = 0;
     std::vector<int32_t> rows;  // rows this rank owns (tile split)
     int last_frames = 0;
@@ -190,14 +206,32 @@ int fail(rt_ctx* c, int code, const std::string& msg) {
         cudaSetDevice(ctx->cfg.device);                                                             \
     } while (0)
 
-Launcher make_launcher(rt_ctx* ctx) {
+// Does the far side of the slab test need its relative widening for rays that start at the camera?  Only when the
+// origin can lie more than ~2.1 grid extents from the grid's corner (rt_scene.cuh, slab1: the rounding of the slab
+// arithmetic then exceeds the builder's guard band); the bound used here is 140 000 of the 65 535 cells.
+bool widen_needed(const rt_ctx* ctx, const rt_uniforms& u) {
+    for (int k = 0; k < 3; k++) {
+        const float r = fabsf(u.defocusDiskRight[k]) + fabsf(u.defocusDiskUp[k]);
+        const float lo = (u.cameraPos[k] - r - ctx->grid[k]) * ctx->grid[3 + k];
+        const float hi = (u.cameraPos[k] + r - ctx->grid[k]) * ctx->grid[3 + k];
+        if (!(fabsf(lo) < 140000.0f) || !(fabsf(hi) < 140000.0f)) return true;
+    }
+    return false;
+}
+
+Launcher make_launcher(rt_ctx* ctx, const rt_uniforms* u = nullptr) {
     Launcher L;
     L.st = ctx->stream;
+    L.top_smem = ctx->top_smem != 0;
+    L.widen_primary = u ? widen_needed(ctx, *u) : true;
+    L.hooks_thread = ctx->hooks_thread != 0;
+    L.shade_bin = ctx->shade_bin != 0;
+    L.shade_oct = ctx->shade_oct != 0;
     L.sm_count = ctx->sm_count;
     L.rng_mode = ctx->cfg.rng_mode;
     L.instrument = ctx->cfg.instrument != 0;
     L.extend_grid = ctx->sm_count * ctx->extend_blocks_per_sm;
-    L.extend_grid_wide = ctx->sm_count * ctx->extend_blocks_per_sm_wide;
+    L.extend_grid_wide = ctx->sm_count * (ctx->top_smem ? ctx->extend_blocks_per_sm_top : ctx->extend_blocks_per_sm_wide);
     L.node_steps_wide = ctx->node_steps_wide;
     L.leaf_vote = ctx->leaf_vote;
     L.refill = ctx->refill;
@@ -218,7 +252,7 @@ SceneView make_view(rt_ctx* ctx) {
     SceneView v;
     memset(&v, 0, sizeof v);
     v.nodes = ctx->p_nodes;
-    v.nodes4 = ctx->wide_ok ? ctx->d_nodes4.as<uint4>() : nullptr;
+    v.nodes4 = ctx->wide_ok ? ctx->p_nodes4 : nullptr;
     for (int k = 0; k < 3; k++) {
         v.grid_lo[k] = ctx->grid[k];
         v.grid_inv[k] = ctx->grid[3 + k];
@@ -234,6 +268,7 @@ SceneView make_view(rt_ctx* ctx) {
         v.tex_ch[i] = ctx->tex_ch[i];
     }
     v.num_tris = (int32_t)ctx->n_tris;
+    v.num_nodes4 = (int32_t)ctx->wide_nodes;
     v.num_materials = ctx->n_mats;
     v.root_is_leaf = ctx->n_tris == 1 ? 1 : 0;
     return v;
@@ -245,7 +280,7 @@ SceneView make_view(rt_ctx* ctx) {
 // a LOSS when the arena does not fit (config 4, 960 MB: a 10 % hitRatio window with streaming misses made
 // the step 18 % slower), so the window is set only when the whole arena fits the persisting carve-out.
 void apply_l2_window(rt_ctx* ctx) {
-    if (!ctx->l2_persist || !ctx->d_bvh.p || ctx->bvh_hot_bytes == 0) return;
+    if (!ctx->l2_persist || !ctx->hot_base || ctx->bvh_hot_bytes == 0) return;
     if (ctx->l2_max_persist < 0) {  // device limits, queried once (cudaGetDeviceProperties costs milliseconds)
         int v = 0;
         ctx->l2_max_persist = cudaDeviceGetAttribute(&v, cudaDevAttrMaxPersistingL2CacheSize, ctx->cfg.device) == cudaSuccess ? v : 0;
@@ -254,7 +289,7 @@ void apply_l2_window(rt_ctx* ctx) {
     }
     if (ctx->l2_max_persist <= 0) return;
     const bool fits = ctx->bvh_hot_bytes <= (size_t)ctx->l2_max_persist && ctx->bvh_hot_bytes <= (size_t)ctx->l2_max_window;
-    const void* base = fits ? ctx->d_bvh.p : nullptr;
+    const void* base = fits ? ctx->hot_base : nullptr;
     const size_t bytes = fits ? ctx->bvh_hot_bytes : 0;
     // a rebuild of the same scene leaves the window as it is: cudaDeviceSetLimit on the persisting carve-out costs
     // tens of milliseconds of host time (measured inside bench.py's end-to-end step)
@@ -265,7 +300,7 @@ void apply_l2_window(rt_ctx* ctx) {
     memset(&attr, 0, sizeof attr);  // num_bytes = 0 disables a window left by a previous, smaller scene
     if (fits) {
         cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, bytes);
-        attr.accessPolicyWindow.base_ptr = ctx->d_bvh.p;
+        attr.accessPolicyWindow.base_ptr = const_cast<void*>(ctx->hot_base);
         attr.accessPolicyWindow.num_bytes = bytes;
         attr.accessPolicyWindow.hitRatio = 1.0f;
         attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
@@ -292,6 +327,8 @@ int validate_uniforms(rt_ctx* ctx, const rt_uniforms* u) {
     if (u->maxBounceCount > kMaxBounces) return fail(ctx, RT_ERR_INVALID, "maxBounceCount too large");
     if (u->basicShading == 0 && u->numRaysPerPixel <= 0) return fail(ctx, RT_ERR_INVALID, "numRaysPerPixel must be > 0");
     if (!ctx->built) return fail(ctx, RT_ERR_STATE, "scene not built: call rt_scene_build first");
+    if (ctx->n_tris > 0 && ctx->max_mat_index >= ctx->n_mats)
+        return fail(ctx, RT_ERR_STATE, "material table smaller than the scene's largest materialIndex");
     return RT_OK;
 }
 
@@ -395,7 +432,7 @@ int render_frames(rt_ctx* ctx, const rt_uniforms& u, uint32_t first, int stride,
     const int W = (int)u.width, H = (int)u.height;
     int rc = prepare_image(ctx, W, H);
     if (rc) return rc;
-    Launcher L = make_launcher(ctx);
+    Launcher L = make_launcher(ctx, &u);
     SceneView sc = make_view(ctx);
     FrameParams fp = make_params(ctx, u);
     if (fp.local_pixels == 0 || count <= 0) return RT_OK;
@@ -547,8 +584,9 @@ int rt_create(rt_ctx** out, const rt_config* cfg) {
         return fail(nullptr, RT_ERR_CUDA, m);
     }
     ctx->stream = ctx->own_stream;
-    ctx->extend_blocks_per_sm = wf_extend_blocks_per_sm(cfg->instrument != 0, false);
-    ctx->extend_blocks_per_sm_wide = wf_extend_blocks_per_sm(cfg->instrument != 0, true);
+    ctx->extend_blocks_per_sm = wf_extend_blocks_per_sm(cfg->instrument != 0, false, false);
+    ctx->extend_blocks_per_sm_wide = wf_extend_blocks_per_sm(cfg->instrument != 0, true, false);
+    ctx->extend_blocks_per_sm_top = wf_extend_blocks_per_sm(false, true, true);
     {
         // Path slots: fewer, larger wavefronts amortise the drain of the persistent kernels (config 2: 8 lanes
         // per pixel 1203 ms/step, 64 lanes 1057 ms).  HBM is there to be used: default 128 Mi slots = 16 GiB,
@@ -569,7 +607,12 @@ int rt_create(rt_ctx** out, const rt_config* cfg) {
     if (const char* e9 = getenv("RT_BVH_WIDTH")) ctx->bvh_width = atoi(e9) == 4 ? 4 : 2;
     if (const char* e5 = getenv("RT_BVH_BUILDER")) ctx->use_ploc = strcmp(e5, "lbvh") != 0;
     if (const char* e4 = getenv("RT_EXT_NODE_STEPS")) ctx->node_steps = std::max(1, std::min(16, atoi(e4)));
-    if (const char* e3 = getenv("RT_EXT_BLOCKS_PER_SM")) ctx->extend_blocks_per_sm = ctx->extend_blocks_per_sm_wide = std::max(1, std::min(32, atoi(e3)));
+    if (const char* e3 = getenv("RT_EXT_BLOCKS_PER_SM"))
+        ctx->extend_blocks_per_sm = ctx->extend_blocks_per_sm_wide = ctx->extend_blocks_per_sm_top = std::max(1, std::min(32, atoi(e3)));
+    if (const char* e11 = getenv("RT_EXT_TOP")) ctx->top_smem = atoi(e11);
+    if (const char* e12 = getenv("RT_SHADE_BIN")) ctx->shade_bin = atoi(e12);
+    if (const char* e13 = getenv("RT_SHADE_OCT")) ctx->shade_oct = atoi(e13);
+    if (const char* e14 = getenv("RT_HOOKS")) ctx->hooks_thread = strcmp(e14, "thread") == 0;
     if (const char* e10 = getenv("RT_EXT_NODE_STEPS_WIDE")) ctx->node_steps_wide = std::max(1, std::min(4, atoi(e10)));
     if (ctx->d_stats.reserve(4 * sizeof(unsigned long long)) != cudaSuccess ||
         cudaMemsetAsync(ctx->d_stats.p, 0, 4 * sizeof(unsigned long long), ctx->stream) != cudaSuccess) {
@@ -590,25 +633,22 @@ void rt_destroy(rt_ctx* ctx) {
     cudaSetDevice(ctx->cfg.device);
     cudaStreamSynchronize(ctx->stream);
     if (ctx->comm && nccl().ok) nccl().CommDestroy(ctx->comm);
-    DevBuf* all[] = {&ctx->d_tris, &ctx->d_mats, &ctx->d_centroid, &ctx->d_bounds, &ctx->d_keys[0], &ctx->d_keys[1],
-                     &ctx->d_vals[0], &ctx->d_vals[1], &ctx->d_hist, &ctx->d_children, &ctx->d_parent, &ctx->d_boxes,
-                     &ctx->d_flags, &ctx->d_depth, &ctx->d_node_depth, &ctx->d_bvh, &ctx->d_grid, &ctx->d_hit,
-                     &ctx->d_contrib, &ctx->d_accum, &ctx->d_pixrng, &ctx->d_counts, &ctx->d_stats, &ctx->d_image,
-                     &ctx->d_sum, &ctx->d_out, &ctx->d_rows, &ctx->d_stage, &ctx->d_compact};
-    for (DevBuf* b : all) b->release();
-    for (auto& b : ctx->d_tex) b.release();
-    for (auto& b : ctx->d_path) b.release();
-    for (auto& b : ctx->d_scratch) b.release();
     for (auto& ev : ctx->events) cudaEventDestroy(ev);
+    for (auto& ev : ctx->build_ev) if (ev) cudaEventDestroy(ev);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
-    delete ctx;
+    delete ctx;  // ~DevBuf releases every device buffer
 }
 
 int rt_set_stream(rt_ctx* ctx, void* cuda_stream) {
     GUARD();
     CK(cudaStreamSynchronize(ctx->stream));
+    if (ctx->l2_win_base) {  // the window is a per-stream attribute: do not leave ours on a stream we hand back
+        cudaStreamAttrValue attr;
+        memset(&attr, 0, sizeof attr);
+        if (cudaStreamSetAttribute(ctx->stream, cudaStreamAttributeAccessPolicyWindow, &attr) != cudaSuccess) cudaGetLastError();
+    }
     ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
-    ctx->l2_win_base = nullptr;  // the window is a per-stream attribute
+    ctx->l2_win_base = nullptr;
     ctx->l2_win_bytes = 0;
     apply_l2_window(ctx);
     return RT_OK;
@@ -618,18 +658,21 @@ int rt_scene_set_triangles(rt_ctx* ctx, const rt_triangle* tris, int64_t count) 
     GUARD();
     if (count < 0 || (count > 0 && !tris)) return fail(ctx, RT_ERR_INVALID, "rt_scene_set_triangles: bad argument");
     if (count > (int64_t)kLeafFirstMask - 8) return fail(ctx, RT_ERR_INVALID, "rt_scene_set_triangles: more than 2^27-9 triangles");
-    CK(ctx->d_tris.reserve(std::max<size_t>((size_t)count, 1) * sizeof(rt_triangle)));
-    if (count) CK(cudaMemcpyAsync(ctx->d_tris.p, tris, (size_t)count * sizeof(rt_triangle), cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));  // glBufferData semantics: the caller may free at once
-    ctx->n_tris = count;
-    ctx->built = false;
-    // material indices are validated on the host copy the caller still owns
+    // validate on the host copy the caller still owns, BEFORE any state of the ctx changes: a rejected call
+    // leaves the previous scene (and its max_mat_index) exactly as it was
     int32_t maxMat = -1, minMat = 0;
     for (int64_t i = 0; i < count; i++) {
         maxMat = std::max(maxMat, tris[i].materialIndex);
         minMat = std::min(minMat, tris[i].materialIndex);
     }
     if (minMat < 0) return fail(ctx, RT_ERR_INVALID, "rt_scene_set_triangles: negative materialIndex");
+    ctx->built = false;  // from here on the old scene is gone, whatever happens
+    ctx->n_tris = 0;
+    ctx->max_mat_index = -1;
+    CK(ctx->d_tris.reserve(std::max<size_t>((size_t)count, 1) * sizeof(rt_triangle)));
+    if (count) CK(cudaMemcpyAsync(ctx->d_tris.p, tris, (size_t)count * sizeof(rt_triangle), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));  // glBufferData semantics: the caller may free at once
+    ctx->n_tris = count;
     ctx->max_mat_index = maxMat;
     return RT_OK;
 }
@@ -637,6 +680,11 @@ int rt_scene_set_triangles(rt_ctx* ctx, const rt_triangle* tris, int64_t count) 
 int rt_scene_set_materials(rt_ctx* ctx, const rt_material* mats, int32_t count) {
     GUARD();
     if (count <= 0 || !mats) return fail(ctx, RT_ERR_INVALID, "rt_scene_set_materials: bad argument");
+    // a built scene keeps rendering with the new table only if every triangle still finds its material
+    if (ctx->built && ctx->n_tris > 0 && ctx->max_mat_index >= count)
+        return fail(ctx, RT_ERR_INVALID, "rt_scene_set_materials: the built scene references material " +
+                                             std::to_string(ctx->max_mat_index) + ", table has " + std::to_string(count));
+    CK(cudaStreamSynchronize(ctx->stream));  // frames in flight still read the old table
     CK(ctx->d_mats.reserve((size_t)count * sizeof(rt_material)));
     CK(cudaMemcpyAsync(ctx->d_mats.p, mats, (size_t)count * sizeof(rt_material), cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
@@ -665,37 +713,46 @@ int rt_scene_build(rt_ctx* ctx) {
         return fail(ctx, RT_ERR_INVALID, "rt_scene_build: a triangle's materialIndex is out of range");
     const int n = (int)ctx->n_tris;
     ctx->built = false;
+    ctx->wide_ok = false;
     if (n == 0) {
         ctx->built = true;
         ctx->bvh_depth = 0;
         return RT_OK;
     }
     const size_t nn = (size_t)std::max(n - 1, 1);
+    const bool wantWide = ctx->bvh_width == 4 && n >= 2;
     CK(ctx->d_centroid.reserve((size_t)n * sizeof(float4)));
     CK(ctx->d_bounds.reserve(12 * sizeof(uint32_t)));
     for (int i = 0; i < 2; i++) {
         CK(ctx->d_keys[i].reserve((size_t)n * sizeof(uint64_t)));
         CK(ctx->d_vals[i].reserve((size_t)n * sizeof(uint32_t)));
     }
-    CK(ctx->d_hist.reserve(sort_hist_entries(n) * sizeof(uint32_t)));
+    CK(ctx->d_hist.reserve(build_scratch_words(n) * sizeof(uint32_t)));
     CK(ctx->d_children.reserve(2 * nn * sizeof(int32_t)));
     CK(ctx->d_parent.reserve((size_t)(2 * n) * sizeof(int32_t)));
     CK(ctx->d_boxes.reserve((size_t)(2 * n) * 2 * sizeof(float4)));
     CK(ctx->d_flags.reserve(((size_t)n + 1) * sizeof(uint32_t)));
     CK(ctx->d_node_depth.reserve((size_t)(2 * n) * sizeof(uint32_t)));
-    CK(ctx->d_depth.reserve(sizeof(uint32_t)));
+    CK(ctx->d_depth.reserve(kBuildStatusWords * sizeof(uint32_t)));
     CK(ctx->d_grid.reserve(6 * sizeof(float)));
+    CK(ctx->d_wide_count.reserve(2 * sizeof(uint32_t)));
     {
+        // one arena, in the order the traversal touches it: binary nodes (hooks, preview, RT_BVH_WIDTH=2) | 4-wide
+        // nodes | triangle records | original indices | shading records.  The L2 persisting window covers what
+        // k_extend gathers from: [wide nodes (or binary nodes when there are none), end of the original indices).
         auto up = [](size_t b) { return (b + 255) & ~(size_t)255; };
-        const size_t bNodes = up(nn * 2 * sizeof(uint4)), bGeom = up((size_t)n * 4 * sizeof(float4)),
-                     bOrig = up((size_t)n * sizeof(int32_t)), bShade = up((size_t)n * 2 * sizeof(float4));
-        CK(ctx->d_bvh.reserve(bNodes + bGeom + bOrig + bShade));
+        const size_t bNodes = up(nn * 2 * sizeof(uint4)), bNodes4 = wantWide ? up(nn * 4 * sizeof(uint4)) : 0,
+                     bGeom = up((size_t)n * 4 * sizeof(float4)), bOrig = up((size_t)n * sizeof(int32_t)),
+                     bShade = up((size_t)n * 2 * sizeof(float4));
+        CK(ctx->d_bvh.reserve(bNodes + bNodes4 + bGeom + bOrig + bShade));
         char* base = ctx->d_bvh.as<char>();
         ctx->p_nodes = reinterpret_cast<uint4*>(base);
-        ctx->p_geom = reinterpret_cast<float4*>(base + bNodes);
-        ctx->p_orig = reinterpret_cast<int32_t*>(base + bNodes + bGeom);
-        ctx->p_shade = reinterpret_cast<float4*>(base + bNodes + bGeom + bOrig);
-        ctx->bvh_hot_bytes = bNodes + bGeom + bOrig;
+        ctx->p_nodes4 = wantWide ? reinterpret_cast<uint4*>(base + bNodes) : nullptr;
+        ctx->p_geom = reinterpret_cast<float4*>(base + bNodes + bNodes4);
+        ctx->p_orig = reinterpret_cast<int32_t*>(base + bNodes + bNodes4 + bGeom);
+        ctx->p_shade = reinterpret_cast<float4*>(base + bNodes + bNodes4 + bGeom + bOrig);
+        ctx->hot_base = wantWide ? (const void*)ctx->p_nodes4 : (const void*)ctx->p_nodes;
+        ctx->bvh_hot_bytes = (wantWide ? bNodes4 : bNodes) + bGeom + bOrig;
     }
     BuildArgs a;
     a.tris = ctx->d_tris.as<rt_triangle>();
@@ -714,53 +771,54 @@ int rt_scene_build(rt_ctx* ctx) {
     a.boxes = ctx->d_boxes.as<float4>();
     a.flags = ctx->d_flags.as<uint32_t>();
     a.nodeDepth = ctx->d_node_depth.as<uint32_t>();
-    a.maxDepth = ctx->d_depth.as<uint32_t>();
+    a.status = ctx->d_depth.as<uint32_t>();
     a.nodes = ctx->p_nodes;
-    a.nodes4 = nullptr;
-    a.wide_count = nullptr;
+    a.nodes4 = ctx->p_nodes4;
+    a.wide_count = wantWide ? ctx->d_wide_count.as<uint32_t>() : nullptr;
     int wideLevels = 0;
     a.wide_levels = &wideLevels;
-    if (ctx->bvh_width == 4 && n >= 2) {
-        CK(ctx->d_nodes4.reserve(nn * 4 * sizeof(uint4)));
-        CK(ctx->d_wide_count.reserve(sizeof(uint32_t)));
-        a.nodes4 = ctx->d_nodes4.as<uint4>();
-        a.wide_count = ctx->d_wide_count.as<uint32_t>();
-    }
     a.grid = ctx->d_grid.as<float>();
     a.geom = ctx->p_geom;
     a.shade = ctx->p_shade;
     a.orig = ctx->p_orig;
-    cudaEvent_t e0, e1;
-    CK(cudaEventCreate(&e0));
-    CK(cudaEventCreate(&e1));
-    CK(cudaEventRecord(e0, ctx->stream));
-    CK(build_lbvh(a, ctx->stream, &ctx->kernel_launches));
-    CK(cudaEventRecord(e1, ctx->stream));
-    uint32_t depth = 0;
-    CK(cudaMemcpyAsync(&depth, ctx->d_depth.p, sizeof depth, cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaMemcpyAsync(ctx->grid, ctx->d_grid.p, sizeof ctx->grid, cudaMemcpyDeviceToHost, ctx->stream));
-    if (a.wide_count) CK(cudaMemcpyAsync(&ctx->wide_nodes, a.wide_count, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
-    float ms = 0.0f;
-    cudaEventElapsedTime(&ms, e0, e1);
-    cudaEventDestroy(e0);
-    cudaEventDestroy(e1);
-    ctx->build_ms = ms;
-    ctx->bvh_depth = depth;
-    if ((int)depth + 1 >= kStackSize && a.use_ploc) {
-        // agglomerative clustering can chain (one big cluster absorbing neighbours round after round);
-        // the Karras tree over the same Morton order is at most key-bits deep
-        a.use_ploc = 0;
+    a.sm_count = ctx->sm_count;
+    for (auto& ev : ctx->build_ev)
+        if (!ev) CK(cudaEventCreate(&ev));
+    uint32_t status[kBuildStatusWords] = {0};
+    uint32_t wide[2] = {0, 0};
+    auto run = [&]() -> int {
+        CK(cudaEventRecord(ctx->build_ev[0], ctx->stream));
         CK(build_lbvh(a, ctx->stream, &ctx->kernel_launches));
-        CK(cudaMemcpyAsync(&depth, ctx->d_depth.p, sizeof depth, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaEventRecord(ctx->build_ev[1], ctx->stream));
+        CK(cudaMemcpyAsync(status, ctx->d_depth.p, sizeof status, cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaMemcpyAsync(ctx->grid, ctx->d_grid.p, sizeof ctx->grid, cudaMemcpyDeviceToHost, ctx->stream));
+        if (a.wide_count) CK(cudaMemcpyAsync(wide, a.wide_count, sizeof wide, cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));
-        ctx->bvh_depth = depth;
+        return RT_OK;
+    };
+    int rc = run();
+    if (rc) return rc;
+    if (status[kBuildNonFinite])
+        return fail(ctx, RT_ERR_INVALID, "rt_scene_build: a triangle has a non-finite vertex coordinate");
+    if (a.use_ploc && (status[kBuildPlocStuck] || (int)status[kBuildDepth] + 1 >= kStackSize)) {
+        // agglomerative clustering can chain (one big cluster absorbing neighbours round after round) or, with
+        // boxes whose union area overflows, find no mutual pair at all; the Karras tree over the same Morton
+        // order is at most key-bits deep and always exists
+        a.use_ploc = 0;
+        rc = run();
+        if (rc) return rc;
     }
-    if ((int)depth + 1 >= kStackSize)
-        return fail(ctx, RT_ERR_INVALID, "rt_scene_build: BVH deeper than the traversal stack (" + std::to_string(depth) + ")");
-    // a 4-wide visit pushes up to three children: the worst-case stack is 3 x (depth of the wide tree)
-    ctx->wide_ok = a.nodes4 != nullptr && wideLevels > 0 && 3 * (wideLevels + 1) < kStackSize;
+    float ms = 0.0f;
+    cudaEventElapsedTime(&ms, ctx->build_ev[0], ctx->build_ev[1]);
+    ctx->build_ms = ms;
+    ctx->bvh_depth = status[kBuildDepth];
+    ctx->build_rounds = a.use_ploc ? status[kBuildPlocRounds] : 0u;
+    if ((int)ctx->bvh_depth + 1 >= kStackSize)
+        return fail(ctx, RT_ERR_INVALID, "rt_scene_build: BVH deeper than the traversal stack (" + std::to_string(ctx->bvh_depth) + ")");
+    // a 4-wide visit pushes at most (children - 1) entries; k_collapse4 tracks the worst root-to-leaf total
+    ctx->wide_nodes = wide[0];
+    ctx->wide_stack_need = wide[1];
+    ctx->wide_ok = a.nodes4 != nullptr && wideLevels > 0 && (int)wide[1] + 2 < kStackSize;
     ctx->wide_depth = wideLevels;
     ctx->built = true;
     apply_l2_window(ctx);
@@ -839,6 +897,21 @@ int rt_screenshot(rt_ctx* ctx, const rt_uniforms* uniforms, int32_t frames, uint
     return rt_screenshot_fetch(ctx, rgb8);
 }
 
+namespace {
+// queue, hit records and counters for a hook over n rays (d_scratch[6..9])
+int hook_buffers(rt_ctx* ctx, size_t n, HookBuffers* hb) {
+    CK(ctx->d_scratch[6].reserve(n * sizeof(float4)));
+    CK(ctx->d_scratch[7].reserve(n * sizeof(float4)));
+    CK(ctx->d_scratch[8].reserve(n * sizeof(float4)));
+    CK(ctx->d_scratch[9].reserve(2 * sizeof(uint32_t)));
+    hb->rays = PathArrays{ctx->d_scratch[6].as<float4>(), ctx->d_scratch[7].as<float4>(), nullptr};
+    hb->hit = ctx->d_scratch[8].as<float4>();
+    hb->counts = ctx->d_scratch[9].as<uint32_t>();
+    hb->stats = ctx->d_stats.as<unsigned long long>();
+    return RT_OK;
+}
+}  // namespace
+
 int rt_first_hit(rt_ctx* ctx, const rt_uniforms* uniforms, int32_t mode, int32_t* tri_id, float* dst) {
     GUARD();
     int rc = validate_uniforms(ctx, uniforms);
@@ -847,6 +920,9 @@ int rt_first_hit(rt_ctx* ctx, const rt_uniforms* uniforms, int32_t mode, int32_t
     const size_t n = (size_t)uniforms->width * uniforms->height;
     CK(ctx->d_scratch[0].reserve(n * sizeof(int32_t)));
     CK(ctx->d_scratch[1].reserve(n * sizeof(float)));
+    HookBuffers hb;
+    rc = hook_buffers(ctx, n, &hb);
+    if (rc) return rc;
     Launcher L = make_launcher(ctx);
     SceneView sc = make_view(ctx);
     FrameParams fp;
@@ -854,7 +930,7 @@ int rt_first_hit(rt_ctx* ctx, const rt_uniforms* uniforms, int32_t mode, int32_t
     fp.u = *uniforms;
     fp.width = (int)uniforms->width;
     fp.height = (int)uniforms->height;
-    CK(wf_first_hit(L, sc, fp, mode, ctx->d_scratch[0].as<int32_t>(), ctx->d_scratch[1].as<float>()));
+    CK(wf_first_hit(L, sc, fp, mode, hb, ctx->d_scratch[0].as<int32_t>(), ctx->d_scratch[1].as<float>()));
     if (tri_id) CK(cudaMemcpyAsync(tri_id, ctx->d_scratch[0].p, n * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
     if (dst) CK(cudaMemcpyAsync(dst, ctx->d_scratch[1].p, n * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
@@ -867,17 +943,21 @@ int rt_trace_rays(rt_ctx* ctx, const float* origins, const float* dirs, int64_t 
     if (!ctx->built) return fail(ctx, RT_ERR_STATE, "scene not built: call rt_scene_build first");
     if (count < 0 || (count > 0 && (!origins || !dirs))) return fail(ctx, RT_ERR_INVALID, "rt_trace_rays: bad argument");
     if (count == 0) return RT_OK;
+    if (count > ((int64_t)1 << 30)) return fail(ctx, RT_ERR_INVALID, "rt_trace_rays: more than 2^30 rays in one call");
     const size_t n = (size_t)count;
     CK(ctx->d_scratch[0].reserve(n * 3 * sizeof(float)));
     CK(ctx->d_scratch[1].reserve(n * 3 * sizeof(float)));
     for (int i = 2; i < 6; i++) CK(ctx->d_scratch[i].reserve(n * sizeof(float)));
+    HookBuffers hb;
+    int rc = hook_buffers(ctx, n, &hb);
+    if (rc) return rc;
     CK(cudaMemcpyAsync(ctx->d_scratch[0].p, origins, n * 3 * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(ctx->d_scratch[1].p, dirs, n * 3 * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
     Launcher L = make_launcher(ctx);
     SceneView sc = make_view(ctx);
-    CK(wf_trace_rays(L, sc, ctx->d_scratch[0].as<float>(), ctx->d_scratch[1].as<float>(), count,
+    CK(wf_trace_rays(L, sc, ctx->d_scratch[0].as<float>(), ctx->d_scratch[1].as<float>(), count, hb,
                      ctx->d_scratch[2].as<int32_t>(), ctx->d_scratch[3].as<float>(), ctx->d_scratch[4].as<float>(),
-                     ctx->d_scratch[5].as<float>(), ctx->d_stats.as<unsigned long long>()));
+                     ctx->d_scratch[5].as<float>()));
     if (tri_id) CK(cudaMemcpyAsync(tri_id, ctx->d_scratch[2].p, n * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
     if (dst) CK(cudaMemcpyAsync(dst, ctx->d_scratch[3].p, n * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
     if (bu) CK(cudaMemcpyAsync(bu, ctx->d_scratch[4].p, n * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
@@ -960,10 +1040,17 @@ int rt_get_counters(rt_ctx* ctx, rt_counters* out) {
     out->bvh_nodes = ctx->n_tris >= 2 ? (uint64_t)ctx->n_tris - 1 : 0;
     out->bvh_bytes = out->bvh_nodes * 32 + (uint64_t)ctx->n_tris * 48;
     out->bvh_depth = ctx->bvh_depth;
+    out->bvh_width = 2;
+    out->extend_blocks_per_sm = (uint64_t)ctx->extend_blocks_per_sm;
+    out->bvh_stack_need = ctx->bvh_depth;
+    out->bvh_build_rounds = ctx->build_rounds;
     if (ctx->wide_ok) {  // what k_extend walks: the 4-wide tree
         out->bvh_nodes = ctx->wide_nodes;
         out->bvh_bytes = (uint64_t)ctx->wide_nodes * 64 + (uint64_t)ctx->n_tris * 48;
         out->bvh_depth = (uint64_t)ctx->wide_depth;
+        out->bvh_width = 4;
+        out->extend_blocks_per_sm = (uint64_t)(ctx->top_smem ? ctx->extend_blocks_per_sm_top : ctx->extend_blocks_per_sm_wide);
+        out->bvh_stack_need = ctx->wide_stack_need;
     }
     return RT_OK;
 }

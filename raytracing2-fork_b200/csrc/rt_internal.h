@@ -18,24 +18,31 @@ struct BuildArgs {
     uint32_t* bounds;         // 12 order-preserving uints
     uint64_t* keys[2];        // n each
     uint32_t* vals[2];        // n each
-    uint32_t* hist;           // sort_hist_entries(n)
+    uint32_t* hist;           // build_scratch_words(n): sort histograms, later PLOC control block + tile states
     int32_t* children;        // 2*(n-1)
     int32_t* parent;          // 2n-1
     float4* boxes;            // 2*(2n-1)
     uint32_t* flags;          // n+1
     uint32_t* nodeDepth;      // 2n (height of the subtree under each inner node / entity)
-    uint32_t* maxDepth;       // 1
+    uint32_t* status;         // kBuildStatusWords: depth of the binary tree + error flags (see below)
+    int sm_count;
     float* grid;              // 6: quantisation grid (output)
     uint4* nodes;             // 2*(n-1)   (output)
     uint4* nodes4;            // 4*(n-1) or NULL: 4-wide nodes collapsed from the binary tree (output)
-    uint32_t* wide_count;     // 1: number of 4-wide nodes written (output, device)
+    uint32_t* wide_count;     // 2: [0] number of 4-wide nodes written, [1] worst-case traversal stack entries (device)
     int* wide_levels;         // host: depth of the 4-wide tree = levels the collapse ran (output)
     float4* geom;             // 4*n       (output)
     float4* shade;            // 2*n       (output)
     int32_t* orig;            // n         (output)
 };
+// status words written by the build (device), read back once by rt_scene_build
+constexpr int kBuildDepth = 0;       // depth of the binary tree
+constexpr int kBuildNonFinite = 1;   // != 0: a vertex coordinate is inf or NaN
+constexpr int kBuildPlocStuck = 2;   // != 0: PLOC found no mutual pair / ran out of rounds (caller falls back to Karras)
+constexpr int kBuildPlocRounds = 3;  // rounds the clustering took (diagnostic)
+constexpr int kBuildStatusWords = 4;
 cudaError_t build_lbvh(const BuildArgs& a, cudaStream_t st, uint64_t* launches);
-size_t sort_hist_entries(int n);
+size_t build_scratch_words(int n);
 
 // ---------------------------------------------------------------- wavefront.cu
 // Path state of the wavefront, structure of arrays, 16-byte records, ping-ponged between bounces
@@ -99,6 +106,14 @@ struct WaveBuffers {
     uint8_t* out_rgb8;    // W*H*3 final, top-down
 };
 
+// queue + results of the parity hooks (rt_first_hit, rt_trace_rays), which run k_extend on caller-defined rays
+struct HookBuffers {
+    PathArrays rays;            // od0 / od1 only
+    float4* hit;
+    uint32_t* counts;           // [0] rays, [1] work cursor
+    unsigned long long* stats;  // the ctx counters (segments, node visits, triangle tests)
+};
+
 struct Launcher {
     cudaStream_t st;
     int sm_count;
@@ -111,6 +126,11 @@ struct Launcher {
     int refill;        // k_extend: refill when this many lanes are idle
     int node_steps;    // k_extend: node steps per vote
     bool speculative;  // k_extend: postponed-leaf variant
+    bool top_smem;     // k_extend (4-wide): root + three levels of the tree staged in shared memory
+    bool widen_primary;  // camera rays may start far outside the quantisation grid (rt_scene.cuh, slab1)
+    bool hooks_thread; // parity hooks walk the binary tree per thread instead of running k_extend
+    bool shade_bin;    // k_shade: block-local material queues
+    bool shade_oct;    // k_shade: block-aggregated, octant-ordered output
     int shade_blocks_per_sm;  // grid-stride k_shade: blocks per SM
     uint64_t* kernel_launches;
     uint64_t* extend_launches;
@@ -122,17 +142,17 @@ struct Launcher {
     bool timing;
 };
 
-int wf_extend_blocks_per_sm(bool instrument, bool wide);
+int wf_extend_blocks_per_sm(bool instrument, bool wide, bool top);
 cudaError_t wf_clear_accum(const Launcher& L, const WaveBuffers& wb, long long entries);
 cudaError_t wf_seed_pixels(const Launcher& L, const SceneView& sc, const WaveBuffers& wb, const FrameParams& fp);
 cudaError_t wf_render_batch(const Launcher& L, const SceneView& sc, const WaveBuffers& wb, const FrameParams& fp);
 cudaError_t wf_resolve_frame(const Launcher& L, const WaveBuffers& wb, const FrameParams& fp, bool add_to_sum);
 cudaError_t wf_preview(const Launcher& L, const SceneView& sc, const WaveBuffers& wb, const FrameParams& fp);
 cudaError_t wf_finalize(const Launcher& L, const uint32_t* frame_sum, uint8_t* out, int w, int h, int frames);
-cudaError_t wf_first_hit(const Launcher& L, const SceneView& sc, const FrameParams& fp, int mode,
+cudaError_t wf_first_hit(const Launcher& L, const SceneView& sc, const FrameParams& fp, int mode, const HookBuffers& hb,
                          int32_t* tri_id, float* dst);
 cudaError_t wf_trace_rays(const Launcher& L, const SceneView& sc, const float* o, const float* d, int64_t n,
-                          int32_t* tri, float* dst, float* bu, float* bv, unsigned long long* stats);
+                          const HookBuffers& hb, int32_t* tri, float* dst, float* bu, float* bv);
 cudaError_t wf_scatter_rows(const Launcher& L, const uint32_t* compact, uint32_t* full, const int32_t* rows,
                             int nrows, int width);
 cudaError_t wf_gather_rows(const Launcher& L, const uint32_t* full, uint32_t* compact, const int32_t* rows,

@@ -35,6 +35,7 @@ struct SceneView {
     const uint8_t* tex_px[5];
     int32_t tex_w[5], tex_h[5], tex_ch[5];
     int32_t num_tris;
+    int32_t num_nodes4;    // 4-wide nodes behind `nodes4`
     int32_t num_materials;
     int32_t root_is_leaf;  // scenes with a single triangle have no inner node
     float grid_lo[3];      // world position of quantised coordinate 0
@@ -50,7 +51,9 @@ struct HitRec {
 #ifndef RT_SLAB_FMA
 #define RT_SLAB_FMA 1
 #endif
-constexpr int kStackSize = 128;
+// traversal stack entries per ray: 16 in shared memory (k_extend), the rest in local memory.  rt_scene_build checks the
+// exact worst case of the tree it built against this (binary: depth; 4-wide: sum of children-1 along the deepest path).
+constexpr int kStackSize = 256;
 // outward rounding margin of the quantised planes, in grid cells (bvh_build.cu k_emit_nodes)
 #if RT_SLAB_FMA
 constexpr float kGuardCells = 0.0625f;
@@ -125,9 +128,14 @@ __device__ __forceinline__ float slab_t(float q, float o, float i) {
 // (RT_SLAB_FMA=0 keeps the subtract-multiply form with a 1e-3 cell guard band.  Selecting near / far planes
 // by direction sign with a byte permute instead of min / max was measured too: 3 more registers cost a
 // resident block per SM and 1.5 %.)
+// WIDEN = false drops the relative widening of the far side: it exists only for origins far outside the grid
+// (|o| beyond ~2.1 grid extents, where the bound above exceeds the guard band); every bounce ray starts on a
+// surface of the scene, i.e. inside the grid, and so does a camera that stands inside or near the scene box —
+// k_extend is instantiated both ways and the host picks per launch (rt_api.cu: widen_needed).
+constexpr float kWidenFar = 1.000001f;
+template <bool WIDEN = true>
 __device__ __forceinline__ void slab2(const uint32_t (&w)[8], const GridRay& g, float bestT, float& lNear,
                                       float& rNear, bool& hitL, bool& hitR) {
-    const float kWiden = 1.000001f;
     const float lx0 = slab_t(q_lo(w[0]), g.ox, g.ix), lx1 = slab_t(q_hi(w[0]), g.ox, g.ix);
     const float ly0 = slab_t(q_lo(w[1]), g.oy, g.iy), ly1 = slab_t(q_hi(w[1]), g.oy, g.iy);
     const float lz0 = slab_t(q_lo(w[2]), g.oz, g.iz), lz1 = slab_t(q_hi(w[2]), g.oz, g.iz);
@@ -136,20 +144,22 @@ __device__ __forceinline__ void slab2(const uint32_t (&w)[8], const GridRay& g, 
     const float rz0 = slab_t(q_lo(w[5]), g.oz, g.iz), rz1 = slab_t(q_hi(w[5]), g.oz, g.iz);
     lNear = fmaxf(fmaxf(fminf(lx0, lx1), fminf(ly0, ly1)), fmaxf(fminf(lz0, lz1), 0.0f));
     rNear = fmaxf(fmaxf(fminf(rx0, rx1), fminf(ry0, ry1)), fmaxf(fminf(rz0, rz1), 0.0f));
-    const float lFar = fminf(fminf(fmaxf(lx0, lx1), fmaxf(ly0, ly1)), fminf(fmaxf(lz0, lz1), bestT)) * kWiden;
-    const float rFar = fminf(fminf(fmaxf(rx0, rx1), fmaxf(ry0, ry1)), fminf(fmaxf(rz0, rz1), bestT)) * kWiden;
+    float lFar = fminf(fminf(fmaxf(lx0, lx1), fmaxf(ly0, ly1)), fminf(fmaxf(lz0, lz1), bestT));
+    float rFar = fminf(fminf(fmaxf(rx0, rx1), fmaxf(ry0, ry1)), fminf(fmaxf(rz0, rz1), bestT));
+    if (WIDEN) { lFar *= kWidenFar; rFar *= kWidenFar; }
     hitL = lNear <= lFar;
     hitR = rNear <= rFar;
 }
 // One slab test against a quantised box (words lo | hi << 16 per axis): entry distance, or kSlabMiss.
 constexpr float kSlabMiss = 3.0e38f;
+template <bool WIDEN = true>
 __device__ __forceinline__ float slab1(uint32_t wx, uint32_t wy, uint32_t wz, const GridRay& g, float bestT) {
-    const float kWiden = 1.000001f;
     const float x0 = slab_t(q_lo(wx), g.ox, g.ix), x1 = slab_t(q_hi(wx), g.ox, g.ix);
     const float y0 = slab_t(q_lo(wy), g.oy, g.iy), y1 = slab_t(q_hi(wy), g.oy, g.iy);
     const float z0 = slab_t(q_lo(wz), g.oz, g.iz), z1 = slab_t(q_hi(wz), g.oz, g.iz);
     const float tn = fmaxf(fmaxf(fminf(x0, x1), fminf(y0, y1)), fmaxf(fminf(z0, z1), 0.0f));
-    const float tf = fminf(fminf(fmaxf(x0, x1), fmaxf(y0, y1)), fminf(fmaxf(z0, z1), bestT)) * kWiden;
+    float tf = fminf(fminf(fmaxf(x0, x1), fmaxf(y0, y1)), fminf(fmaxf(z0, z1), bestT));
+    if (WIDEN) tf *= kWidenFar;
     return tn <= tf ? tn : kSlabMiss;
 }
 // first 48 bytes of a triangle record: a, e0, e1, N
@@ -196,7 +206,6 @@ __device__ __forceinline__ bool ray_triangle(V3 o, V3 d, V3 a, V3 e0, V3 e1, V3 
 // Leaf children are packed into one negative int: child = ~(first | (count-1) << 27).
 constexpr int kLeafCountShift = 27;
 constexpr int32_t kLeafFirstMask = (1 << kLeafCountShift) - 1;
-constexpr int kMaxLeafTris = 16;
 __host__ __device__ __forceinline__ int32_t pack_leaf(int32_t first, int32_t count) {
     return ~(first | ((count - 1) << kLeafCountShift));
 }

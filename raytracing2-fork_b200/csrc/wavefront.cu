@@ -248,7 +248,9 @@ __global__ void __launch_bounds__(kBlock) k_raygen(const __grid_constant__ Frame
     cur.od0[i] = make_float4(o.x, o.y, o.z, d.x);
     cur.od1[i] = make_float4(d.y, d.z, 1.0f, 1.0f);
     cur.misc[i] = make_float4(1.0f, __int_as_float(i), __uint_as_float(rng.carry()), __int_as_float(0));
-    contrib[i] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    // every path writes its slot of `contrib` exactly once, at its terminal event in k_shade (the bounce limit is
+    // one); only a frame without any bounce needs the zero
+    if (fp.u.maxBounceCount <= 0) contrib[i] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
 }
 
 // ---------------------------------------------------------------------------------------------- k_extend
@@ -313,13 +315,13 @@ struct Stack {
         else { const int2 e = sh[sp * kExtBlock]; c = e.x; t = __int_as_float(e.y); }
     }
 };
-template <bool DEEP>
+template <bool DEEP, bool WIDEN>
 __device__ __forceinline__ void node_step(const SceneView& sc, const RayRegs& r, int32_t& node, int& sp, Stack& st) {
     uint32_t w[8];
     ldg256u(sc.nodes + 2 * node, w);
     float lNear, rNear;
     bool hitL, hitR;
-    slab2(w, r.g, r.bestT, lNear, rNear, hitL, hitR);
+    slab2<WIDEN>(w, r.g, r.bestT, lNear, rNear, hitL, hitR);
     const int32_t cl = (int32_t)w[6], cr = (int32_t)w[7];
     // a missed child is infinitely far: the near / far choice, "both" and "any" then come out of one compare,
     // one min and one max instead of a predicate ladder
@@ -337,17 +339,27 @@ __device__ __forceinline__ void node_step(const SceneView& sc, const RayRegs& r,
 // The same step over a 4-wide node (64 bytes, two 256-bit loads): four slab tests, a 5-comparator sorting network
 // on (entry distance, child) with missed children at +inf, the nearest child becomes the lane's node and the other
 // hit children are pushed farthest first.  Up to three pushes per step.
-template <bool DEEP>
-__device__ __forceinline__ void node_step4(const SceneView& sc, const RayRegs& r, int32_t& node, int& sp, Stack& st) {
+// TOP: the first kTopNodes wide nodes (k_collapse4 numbers them level by level, so these are the root and the three
+// levels below it: 1 + 4 + 16 + 64) are read from the block's shared-memory copy instead of L1 / L2.
+constexpr int kTopNodes = 85;
+template <bool DEEP, bool WIDEN, bool TOP>
+__device__ __forceinline__ void node_step4(const SceneView& sc, const uint4* __restrict__ sTop, const RayRegs& r,
+                                           int32_t& node, int& sp, Stack& st) {
     uint32_t a[8], b[8];
-    ldg256u(sc.nodes4 + 4 * node, a);
-    ldg256u(sc.nodes4 + 4 * node + 2, b);
+    if (TOP && node < kTopNodes) {
+        const uint4 q0 = sTop[4 * node + 0], q1 = sTop[4 * node + 1], q2 = sTop[4 * node + 2], q3 = sTop[4 * node + 3];
+        a[0] = q0.x; a[1] = q0.y; a[2] = q0.z; a[3] = q0.w; a[4] = q1.x; a[5] = q1.y; a[6] = q1.z; a[7] = q1.w;
+        b[0] = q2.x; b[1] = q2.y; b[2] = q2.z; b[3] = q2.w; b[4] = q3.x; b[5] = q3.y; b[6] = q3.z; b[7] = q3.w;
+    } else {
+        ldg256u(sc.nodes4 + 4 * node, a);
+        ldg256u(sc.nodes4 + 4 * node + 2, b);
+    }
     float t[4];
     int32_t c[4] = {(int32_t)b[4], (int32_t)b[5], (int32_t)b[6], (int32_t)b[7]};
-    t[0] = slab1(a[0], a[1], a[2], r.g, r.bestT);
-    t[1] = slab1(a[3], a[4], a[5], r.g, r.bestT);
-    t[2] = slab1(a[6], a[7], b[0], r.g, r.bestT);
-    t[3] = slab1(b[1], b[2], b[3], r.g, r.bestT);
+    t[0] = slab1<WIDEN>(a[0], a[1], a[2], r.g, r.bestT);
+    t[1] = slab1<WIDEN>(a[3], a[4], a[5], r.g, r.bestT);
+    t[2] = slab1<WIDEN>(a[6], a[7], b[0], r.g, r.bestT);
+    t[3] = slab1<WIDEN>(b[1], b[2], b[3], r.g, r.bestT);
 #define RT_CE(i, j)                                   \
     {                                                 \
         const bool sw = t[j] < t[i];                  \
@@ -373,7 +385,7 @@ __device__ __forceinline__ bool is_leaf_code(int32_t x) { return x < 0 && (uint3
 // `post` and keeps descending; it only has to wait for a leaf step when it reaches a SECOND leaf (or runs
 // out of nodes).  Node steps then run with more lanes, leaf steps test up to two leaves per lane; the price
 // is a stale bestT while a leaf is parked (a few more node visits).  Selected at run time (RT_EXT_SPEC).
-template <bool COUNT, bool SPEC, bool WIDE>
+template <bool COUNT, bool SPEC, bool WIDE, bool WIDEN, bool TOP>
 __global__ void __launch_bounds__(kExtBlock) k_extend(const __grid_constant__ SceneView sc, PathArrays cur,
                                                       float4* __restrict__ hit, const uint32_t* __restrict__ count,
                                                       uint32_t* __restrict__ cursor, ExtendTune tune,
@@ -383,9 +395,15 @@ __global__ void __launch_bounds__(kExtBlock) k_extend(const __grid_constant__ Sc
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t ltMask = (1u << lane) - 1u;
     constexpr uint32_t FULL = 0xffffffffu;
-    const float kWiden = 1.000001f;
+    const float kWiden = WIDEN ? kWidenFar : 1.0f;  // x * 1.0f folds away
 
     __shared__ int2 shStack[kShStack][kExtBlock];
+    __shared__ uint4 sTop[TOP ? 4 * kTopNodes : 1];
+    if (TOP) {
+        const int have = min(4 * kTopNodes, 4 * sc.num_nodes4);
+        for (int k = threadIdx.x; k < have; k += kExtBlock) sTop[k] = __ldg(&sc.nodes4[k]);
+        __syncthreads();
+    }
     int32_t ovNode[kStackSize - kShStack];
     float ovT[kStackSize - kShStack];
     Stack st{&shStack[0][threadIdx.x], ovNode, ovT};
@@ -456,8 +474,8 @@ __global__ void __launch_bounds__(kExtBlock) k_extend(const __grid_constant__ Sc
         }
         if (node >= 0) {
             if (COUNT) visits++;
-            if (WIDE) node_step4<DEEP>(sc, r, node, sp, st);
-            else node_step<DEEP>(sc, r, node, sp, st);
+            if (WIDE) node_step4<DEEP, WIDEN, TOP>(sc, sTop, r, node, sp, st);
+            else node_step<DEEP, WIDEN>(sc, r, node, sp, st);
             if (SPEC) {
                 const bool park = is_leaf_code(node) & (post == kNoLeaf);
                 post = park ? node : post;
@@ -580,9 +598,22 @@ __device__ __forceinline__ BounceRandoms bounce_randoms(Rng<0>& rng, bool needDi
 // rejection loop and the on-demand block generation.  Only the 1.2 % of lanes whose first six tries all
 // fail continue in the sequential loop (from draw 18).  Values and draw indices are identical to the
 // sequential definition, so no bit of the image changes.
+// The acceptance test of S:180, `length(v) < 1`, is evaluated as `dot(v, v) < 1`: sqrt is correctly rounded and
+// monotonic, the largest float below 1 is 1 - 2^-24 and sqrt(1 - 2^-24) = 1 - 2^-25 - 2^-51 - ... lies below the
+// midpoint of (1 - 2^-24, 1), so it rounds to a value < 1; for x >= 1, sqrt(x) >= 1.  Same decision, no sqrt
+// (tests/test_oracle_cpu.py::test_rejection_test_without_sqrt).
 __device__ __forceinline__ BounceRandoms bounce_randoms(Rng<1>& rng, bool needDir, int nExtra) {
     constexpr int kBlocks = 5;            // 20 draws: six rejection tries (18) + the two draws after the last
     constexpr int kTries = 6;             // P(all six fail) = 0.476^6 = 1.2 % of lanes take the sequential tail
+    BounceRandoms r;
+    r.randDir = v3(0.0f, 0.0f, 0.0f);
+    if (!__any_sync(0xffffffffu, needDir)) {  // a warp of glass (or finished) paths: draws 0 and 1 only
+        uint32_t w[4];
+        philox4x32_10(0u, rng.bounce, rng.sample, 0x52543230u, rng.pixel, rng.frame, w);
+        r.d0 = u32_to_unit(w[0]);
+        r.d1 = u32_to_unit(w[1]);
+        return r;
+    }
     float f[4 * kBlocks];
     uint32_t lastBlock[4] = {0u, 0u, 0u, 0u};
 #pragma unroll
@@ -596,8 +627,6 @@ __device__ __forceinline__ BounceRandoms bounce_randoms(Rng<1>& rng, bool needDi
             for (int k = 0; k < 4; k++) lastBlock[k] = w[k];
         }
     }
-    BounceRandoms r;
-    r.randDir = v3(0.0f, 0.0f, 0.0f);
     r.d0 = f[0];
     r.d1 = f[1];
     if (needDir) {
@@ -608,7 +637,7 @@ __device__ __forceinline__ BounceRandoms bounce_randoms(Rng<1>& rng, bool needDi
 #pragma unroll
         for (int t = 0; t < kTries; t++) {
             const V3 cand = v3(f[3 * t] * 2.0f - 1.0f, f[3 * t + 1] * 2.0f - 1.0f, f[3 * t + 2] * 2.0f - 1.0f);
-            const bool acc = !found && length(cand) < 1.0f;
+            const bool acc = !found && dot(cand, cand) < 1.0f;
             if (acc) {
                 c = cand;
                 d0 = f[3 * t + 3];
@@ -628,7 +657,7 @@ __device__ __forceinline__ BounceRandoms bounce_randoms(Rng<1>& rng, bool needDi
                 const float x = rng.next() * 2.0f - 1.0f;
                 const float y = rng.next() * 2.0f - 1.0f;
                 const float z = rng.next() * 2.0f - 1.0f;
-                if (length(v3(x, y, z)) < 1.0f) {
+                if (dot(v3(x, y, z), v3(x, y, z)) < 1.0f) {
                     r.randDir = normalize(v3(x, y, z));
                     break;
                 }
@@ -640,55 +669,143 @@ __device__ __forceinline__ BounceRandoms bounce_randoms(Rng<1>& rng, bool needDi
     return r;
 }
 
+// ---------------------------------------------------------------------------------------------- k_shade
+// Block-local queues.  The material switch of S:499-541 diverges per lane (ncu, round 1: 17.6 of 32 lanes per
+// instruction in k_shade), so every block first sorts the 256 paths of its window by MATERIAL CLASS — ballots and
+// popcounts per warp, one prefix over the (warp, class) counts — and thread t then shades the t-th path of that
+// order: warps are (nearly) homogeneous in the switch, in the texture fetch and in whether they need random numbers at
+// all (terminal paths: miss, light, unknown material).  The queue lives in shared memory and costs no HBM traffic: the
+// sorted loads stay inside the block's 4 KB windows of the path arrays.
+// The survivors leave the block the same way: ordered by the OCTANT of their new direction and appended to the next
+// queue with ONE atomicAdd per block, so that the warps of the next k_extend launch receive rays that start close
+// together (same block of the previous queue) and walk the tree in the same near / far order.
+enum { kClsTerminal = 0, kClsDiffuse = 1, kClsTexture = 2, kClsSpecular = 3, kClsGlass = 4, kClsInvalid = 5, kNumCls = 6 };
+__device__ __forceinline__ int material_class(int32_t type) {
+    switch (type) {
+        case RT_MAT_DIFFUSE:
+        case RT_MAT_CHECKER: return kClsDiffuse;
+        case RT_MAT_TEXTURE: return kClsTexture;
+        case RT_MAT_SPECULAR: return kClsSpecular;
+        case RT_MAT_GLASS: return kClsGlass;
+        default: return kClsTerminal;  // LIGHT, GLASS_HIGHLIGHT and unknown types end the path (S:515-520,539-540)
+    }
+}
+template <int NB>
+struct BlockBins {
+    uint32_t cnt[kBlock / 32][NB];  // per (warp, bin): count, then the exclusive prefix over the warps
+    uint32_t tot[NB];
+};
+// Position of this thread in the block's stable counting sort by `key` (0 <= key < NB).  Two block barriers;
+// s.tot holds the bin totals afterwards.
+template <int NB>
+__device__ __forceinline__ uint32_t block_sort_pos(int key, BlockBins<NB>& s) {
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    uint32_t mine = 0u;
+#pragma unroll
+    for (int b = 0; b < NB; b++) {
+        const uint32_t m = __ballot_sync(0xffffffffu, key == b);
+        if (key == b) mine = m;
+        if ((int)lane == b) s.cnt[warp][b] = (uint32_t)__popc(m);
+    }
+    const uint32_t below = (uint32_t)__popc(mine & ((1u << lane) - 1u));
+    __syncthreads();
+    if (threadIdx.x < NB) {
+        uint32_t run = 0u;
+#pragma unroll
+        for (int w = 0; w < kBlock / 32; w++) {
+            const uint32_t c = s.cnt[w][threadIdx.x];
+            s.cnt[w][threadIdx.x] = run;
+            run += c;
+        }
+        s.tot[threadIdx.x] = run;
+    }
+    __syncthreads();
+    uint32_t base = 0u;
+#pragma unroll
+    for (int b = 0; b < NB; b++) base += (b < key) ? s.tot[b] : 0u;
+    return base + s.cnt[warp][key] + below;
+}
+
 // One bounce of S:481-560 for every live path.  `bounce` is the 0-based index of this segment.
-template <int MODE>
+// BIN: block-local material queues; OCT: block-aggregated, octant-ordered output (both change only the order in which
+// paths are processed and stored, never a value: every path's arithmetic is the same, the image is independent of it).
+template <int MODE, bool BIN, bool OCT>
 __global__ void __launch_bounds__(kBlock, 4) k_shade(const __grid_constant__ SceneView sc,
                                                   const __grid_constant__ FrameParams fp, PathArrays cur,
                                                   PathArrays next, const float4* __restrict__ hit,
                                                   float4* __restrict__ contrib, uint32_t* __restrict__ pix_rng,
                                                   const uint32_t* __restrict__ countIn,
                                                   uint32_t* __restrict__ countOut, int bounce) {
+    __shared__ BlockBins<kNumCls> sBin;
+    __shared__ BlockBins<9> sOct;
+    __shared__ uint16_t sOrder[kBlock];
+    __shared__ uint32_t sBase;
     const uint32_t n = *countIn;
     const uint32_t lane = threadIdx.x & 31u;
-    const uint32_t stride = gridDim.x * blockDim.x;
-    for (uint32_t base = blockIdx.x * blockDim.x + (threadIdx.x & ~31u); base < n; base += stride) {
-        const uint32_t i = base + lane;
+    constexpr uint32_t FULL = 0xffffffffu;
+    for (uint32_t base = blockIdx.x * kBlock; base < n; base += gridDim.x * kBlock) {
+        uint32_t i = base + threadIdx.x;
+        if (BIN) {
+            int cls = kClsInvalid;
+            if (i < n) {
+                const int32_t hs = __float_as_int(__ldg(&hit[i].w));
+                cls = kClsTerminal;
+                if (hs >= 0) {
+                    const int32_t mi = __float_as_int(__ldg(&sc.tri_geom[4 * hs + 3].w));
+                    cls = material_class(__float_as_int(__ldg(&sc.materials[6 * mi + 4].z)));
+                }
+            }
+            const uint32_t pos = block_sort_pos<kNumCls>(cls, sBin);
+            sOrder[pos] = (uint16_t)threadIdx.x;
+            __syncthreads();
+            i = base + sOrder[threadIdx.x];  // threads beyond the live count sort last and keep an index >= n
+        }
         const bool valid = i < n;
         bool alive = false;
         V3 o = v3(0, 0, 0), d = v3(0, 0, 1), rayColor = v3(0, 0, 0);
-        int32_t slotId = 0;
+        int32_t slotId = 0, hslot = -1, pixLocal = 0, batchFrame = 0;
         uint32_t carry = 0, flags = 0;
+        bool insideGlass = false;
+        float4 h = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        float4 g3 = make_float4(0.0f, 0.0f, 0.0f, 0.0f);  // unit normal + material index of the hit triangle
+        Material m;
+        m.type = -1;
+        Rng<MODE> rng;
+        rng.init(0u, 0u, 0u, 0u);
+        const int bounceCount = bounce + 1;  // S:483
         if (valid) {
-            const float4 a = cur.od0[i], b = cur.od1[i], c = cur.misc[i], h = hit[i];
+            const float4 a = cur.od0[i], b = cur.od1[i], c = cur.misc[i];
+            h = hit[i];
             o = v3(a.x, a.y, a.z);
             d = v3(a.w, b.x, b.y);
             rayColor = v3(b.z, b.w, c.x);
             slotId = __float_as_int(c.y);
             carry = __float_as_uint(c.z);
             flags = __float_as_uint(c.w);
-            bool insideGlass = (flags >> 16) & 1u;
-            const int bounceCount = bounce + 1;  // S:483
+            insideGlass = (flags >> 16) & 1u;
             const int slotLane = (int)fastdiv((uint32_t)slotId, fp.div_pixels);
-            const int pixLocal = slotId - slotLane * fp.local_pixels;
-            const int batchFrame = fp.frames_in_batch > 1 ? (int)fastdiv((uint32_t)slotLane, fp.div_samples) : 0;
-            Rng<MODE> rng;
+            pixLocal = slotId - slotLane * fp.local_pixels;
+            batchFrame = fp.frames_in_batch > 1 ? (int)fastdiv((uint32_t)slotLane, fp.div_samples) : 0;
             rng.init(carry, local_pixel_id(fp, pixLocal), fp.u.frameIndex + (uint32_t)(batchFrame * fp.frame_stride), 0u);
-            rng.stream((uint32_t)bounceCount);
-
-            const int32_t hslot = __float_as_int(h.w);
-            bool terminated = false;
-            V3 radiance = v3(0.0f, 0.0f, 0.0f);
-            Material m;
-            m.type = -1;
-            float4 g3 = make_float4(0.0f, 0.0f, 0.0f, 0.0f);  // unit normal + material index of the hit triangle
+            hslot = __float_as_int(h.w);
             if (hslot >= 0) {
                 g3 = __ldg(&sc.tri_geom[4 * hslot + 3]);
                 m = load_material(sc, __float_as_int(g3.w));
             }
-            const bool needDir = hslot >= 0 && (m.type == RT_MAT_DIFFUSE || m.type == RT_MAT_TEXTURE ||
-                                                m.type == RT_MAT_SPECULAR || m.type == RT_MAT_CHECKER);
-            const int nExtra = (hslot < 0) ? 0 : (m.type == RT_MAT_SPECULAR ? 2 : ((needDir || m.type == RT_MAT_GLASS) ? 1 : 0));
-            const BounceRandoms rnd = bounce_randoms(rng, needDir, nExtra);
+        }
+        rng.stream((uint32_t)bounceCount);
+        const bool needDir = hslot >= 0 && (m.type == RT_MAT_DIFFUSE || m.type == RT_MAT_TEXTURE ||
+                                            m.type == RT_MAT_SPECULAR || m.type == RT_MAT_CHECKER);
+        const int nExtra = (hslot < 0) ? 0 : (m.type == RT_MAT_SPECULAR ? 2 : ((needDir || m.type == RT_MAT_GLASS) ? 1 : 0));
+        // the random numbers of the bounce, drawn by the whole warp together (lock-step Philox blocks); a warp of
+        // terminal paths draws nothing
+        BounceRandoms rnd;
+        rnd.randDir = v3(0.0f, 0.0f, 0.0f);
+        rnd.d0 = rnd.d1 = 0.0f;
+        if (MODE == 0 || __any_sync(FULL, needDir || nExtra > 0)) rnd = bounce_randoms(rng, needDir, nExtra);
+        if (valid) {
+            bool terminated = false;
+            V3 radiance = v3(0.0f, 0.0f, 0.0f);
             if (hslot >= 0) {
                 const float dst = h.x, bu = h.y, bv = h.z;
                 const V3 hitPoint = o + d * dst;        // S:330
@@ -771,21 +888,36 @@ __global__ void __launch_bounds__(kBlock, 4) k_shade(const __grid_constant__ Sce
                 flags = (uint32_t)bounceCount | ((insideGlass ? 1u : 0u) << 16);
             }
         }
-        // compaction: survivors of this warp take consecutive places in the next queue
-        const uint32_t mask = __ballot_sync(0xffffffffu, alive);
-        if (mask) {
-            uint32_t basePos = 0;
-            const int leader = __ffs(mask) - 1;
-            if ((int)lane == leader) basePos = atomicAdd(countOut, (uint32_t)__popc(mask));
-            basePos = __shfl_sync(0xffffffffu, basePos, leader);
-            if (alive) {
-                const uint32_t pos = basePos + __popc(mask & ((1u << lane) - 1u));
-                next.od0[pos] = make_float4(o.x, o.y, o.z, d.x);
-                next.od1[pos] = make_float4(d.y, d.z, rayColor.x, rayColor.y);
-                next.misc[pos] = make_float4(rayColor.z, __int_as_float(slotId), __uint_as_float(carry),
-                                             __uint_as_float(flags));
+        // compaction: survivors take consecutive places in the next queue
+        uint32_t pos = 0u;
+        if (OCT) {
+            const int key = alive ? ((d.x < 0.0f ? 1 : 0) | (d.y < 0.0f ? 2 : 0) | (d.z < 0.0f ? 4 : 0)) : 8;
+            pos = block_sort_pos<9>(key, sOct);
+            if (threadIdx.x == 0) {
+                uint32_t total = 0u;
+#pragma unroll
+                for (int b = 0; b < 8; b++) total += sOct.tot[b];
+                sBase = total ? atomicAdd(countOut, total) : 0u;
             }
+            __syncthreads();
+            pos += sBase;
+        } else {
+            const uint32_t mask = __ballot_sync(FULL, alive);
+            uint32_t basePos = 0;
+            if (mask) {
+                const int leader = __ffs(mask) - 1;
+                if ((int)lane == leader) basePos = atomicAdd(countOut, (uint32_t)__popc(mask));
+                basePos = __shfl_sync(FULL, basePos, leader);
+            }
+            pos = basePos + __popc(mask & ((1u << lane) - 1u));
         }
+        if (alive) {
+            next.od0[pos] = make_float4(o.x, o.y, o.z, d.x);
+            next.od1[pos] = make_float4(d.y, d.z, rayColor.x, rayColor.y);
+            next.misc[pos] = make_float4(rayColor.z, __int_as_float(slotId), __uint_as_float(carry),
+                                         __uint_as_float(flags));
+        }
+        if (BIN || OCT) __syncthreads();  // the shared queues are rewritten by the next window
     }
 }
 
@@ -941,6 +1073,56 @@ __global__ void __launch_bounds__(kBlock) k_preview(const __grid_constant__ Scen
     if ((threadIdx.x & 31) == 0) atomicAdd(&stats[0], (unsigned long long)segs);
 }
 
+// ---- parity hooks.  Since round 2 they run the TIMED traversal kernel: the rays are packed into a queue, k_extend
+// finds the closest hits, and a small kernel turns (t, u, v, sorted slot) into what the C-ABI reports.  (With
+// RT_HOOKS=thread they use the per-thread binary-tree walk `closest_hit` of rt_scene.cuh instead, the code path of
+// the preview kernel — the two must agree, tests/test_gpu_parity.py.)
+template <int MODE>
+__global__ void __launch_bounds__(kBlock) k_first_rays(const __grid_constant__ FrameParams fp, int mode, PathArrays rays) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= fp.width * fp.height) return;
+    const int ty = p / fp.width, tx = p - ty * fp.width;
+    const PixelSetup ps = pixel_setup(fp.u, tx, ty);
+    V3 o, d;
+    if (mode == RT_FIRST_HIT_CENTRE) {
+        o = v3(fp.u.cameraPos);
+        d = ps.centreDir;
+    } else {
+        Rng<MODE> rng;
+        rng.init(MODE == 0 ? ps.seed : 0u, ps.pixelId, fp.u.frameIndex, 0u);
+        rng.stream(0u);
+        sample_ray(fp.u, ps, rng, o, d);
+    }
+    rays.od0[p] = make_float4(o.x, o.y, o.z, d.x);
+    rays.od1[p] = make_float4(d.y, d.z, 0.0f, 0.0f);
+}
+__global__ void __launch_bounds__(kBlock) k_pack_rays(const float* __restrict__ o3, const float* __restrict__ d3,
+                                                      long long n, PathArrays rays) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    rays.od0[i] = make_float4(o3[3 * i], o3[3 * i + 1], o3[3 * i + 2], d3[3 * i]);
+    rays.od1[i] = make_float4(d3[3 * i + 1], d3[3 * i + 2], 0.0f, 0.0f);
+}
+__global__ void __launch_bounds__(kBlock) k_unpack_hits(const __grid_constant__ SceneView sc,
+                                                        const float4* __restrict__ hit, long long n,
+                                                        int32_t* __restrict__ tri, float* __restrict__ dst,
+                                                        float* __restrict__ bu, float* __restrict__ bv) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float4 h = hit[i];
+    const int32_t slot = __float_as_int(h.w);
+    if (tri) tri[i] = slot >= 0 ? __ldg(&sc.tri_orig[slot]) : -1;
+    if (dst) dst[i] = h.x;
+    if (bu) bu[i] = slot >= 0 ? h.y : 0.0f;
+    if (bv) bv[i] = slot >= 0 ? h.z : 0.0f;
+}
+__global__ void k_hook_count(uint32_t* counts, uint32_t n) {
+    if (threadIdx.x == 0) {
+        counts[0] = n;   // rays in the queue
+        counts[1] = 0u;  // k_extend's work cursor
+    }
+}
+
 template <int MODE>
 __global__ void __launch_bounds__(kBlock) k_first_hit(const __grid_constant__ SceneView sc,
                                                       const __grid_constant__ FrameParams fp, int mode,
@@ -1024,16 +1206,41 @@ struct Timed {
     }
 };
 
-int wf_extend_blocks_per_sm(bool instrument, bool wide) {
+int wf_extend_blocks_per_sm(bool instrument, bool wide, bool top) {
     int nb = 0;
     cudaError_t e;
-    if (wide)
-        e = instrument ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_extend<true, false, true>, kExtBlock, 0)
-                       : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_extend<false, true, true>, kExtBlock, 0);
+    if (wide && top)
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_extend<false, true, true, false, true>, kExtBlock, 0);
+    else if (wide)
+        e = instrument ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_extend<true, false, true, true, false>, kExtBlock, 0)
+                       : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_extend<false, true, true, false, false>, kExtBlock, 0);
     else
-        e = instrument ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_extend<true, false, false>, kExtBlock, 0)
-                       : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_extend<false, true, false>, kExtBlock, 0);
+        e = instrument ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_extend<true, false, false, true, false>, kExtBlock, 0)
+                       : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_extend<false, true, false, false, false>, kExtBlock, 0);
     return e == cudaSuccess && nb > 0 ? nb : 4;
+}
+
+// One closest-hit pass over the `*count` rays of `rays` (od0 / od1): the persistent traversal kernel in the variant
+// the scene and the launch call for.  `widen`: origins may lie far outside the quantisation grid (rt_scene.cuh).
+static void launch_extend(const Launcher& L, const SceneView& sc, const PathArrays& rays, float4* hit,
+                          const uint32_t* count, uint32_t* cursor, bool widen, unsigned long long* stats) {
+    const bool wide = sc.nodes4 != nullptr;
+    ExtendTune tune{L.leaf_vote, L.refill, wide ? L.node_steps_wide : L.node_steps};
+    const int grid = wide ? L.extend_grid_wide : L.extend_grid;
+    cudaStream_t st = L.st;
+#define RT_EXT(C, S, W, WD, T) k_extend<C, S, W, WD, T><<<grid, kExtBlock, 0, st>>>(sc, rays, hit, count, cursor, tune, stats)
+    if (wide) {
+        if (L.instrument) RT_EXT(true, false, true, true, false);
+        else if (L.top_smem) { if (widen) RT_EXT(false, true, true, true, true); else RT_EXT(false, true, true, false, true); }
+        else { if (widen) RT_EXT(false, true, true, true, false); else RT_EXT(false, true, true, false, false); }
+    } else {
+        if (L.instrument) RT_EXT(true, false, false, true, false);
+        else if (!L.speculative) RT_EXT(false, false, false, true, false);
+        else { if (widen) RT_EXT(false, true, false, true, false); else RT_EXT(false, true, false, false, false); }
+    }
+#undef RT_EXT
+    (*L.kernel_launches)++;
+    (*L.extend_launches)++;
 }
 
 cudaError_t wf_clear_accum(const Launcher& L, const WaveBuffers& wb, long long entries) {
@@ -1063,38 +1270,31 @@ cudaError_t wf_render_batch(const Launcher& L, const SceneView& sc, const WaveBu
     // fixed-size grids that read the live count on the device: no host round trip per bounce
     const long long gridCap = (long long)L.sm_count * L.shade_blocks_per_sm;
     const int grid = (int)((n + kBlock - 1) / kBlock < gridCap ? (n + kBlock - 1) / kBlock : gridCap);
-    const int extGrid = L.extend_grid;
     uint32_t* cursors = wb.counts + ncounts;
-    ExtendTune tune{L.leaf_vote, L.refill, L.node_steps};
     PathArrays a = wb.cur, b = wb.next;
     for (int bounce = 0; bounce < maxB; bounce++) {
         {
             Timed t(L, 0);
-            const bool wide = sc.nodes4 != nullptr;
-            ExtendTune tw = tune;
-            tw.nodeSteps = L.node_steps_wide;
-            const int wideGrid = L.extend_grid_wide;
-            if (wide && L.instrument)
-                k_extend<true, false, true><<<wideGrid, kExtBlock, 0, L.st>>>(sc, a, wb.hit, wb.counts + bounce, cursors + bounce, tw, wb.stats);
-            else if (wide)
-                k_extend<false, true, true><<<wideGrid, kExtBlock, 0, L.st>>>(sc, a, wb.hit, wb.counts + bounce, cursors + bounce, tw, wb.stats);
-            else if (L.instrument)
-                k_extend<true, false, false><<<extGrid, kExtBlock, 0, L.st>>>(sc, a, wb.hit, wb.counts + bounce, cursors + bounce, tune, wb.stats);
-            else if (L.speculative)
-                k_extend<false, true, false><<<extGrid, kExtBlock, 0, L.st>>>(sc, a, wb.hit, wb.counts + bounce, cursors + bounce, tune, wb.stats);
-            else
-                k_extend<false, false, false><<<extGrid, kExtBlock, 0, L.st>>>(sc, a, wb.hit, wb.counts + bounce, cursors + bounce, tune, wb.stats);
-            (*L.kernel_launches)++;
-            (*L.extend_launches)++;
+            // camera rays may start far outside the scene; every later segment starts on a surface of it
+            launch_extend(L, sc, a, wb.hit, wb.counts + bounce, cursors + bounce, bounce == 0 ? L.widen_primary : false, wb.stats);
         }
         {
             Timed t(L, 1);
-            if (L.rng_mode == RT_RNG_REF_PCG)
-                k_shade<0><<<grid, kBlock, 0, L.st>>>(sc, fp, a, b, wb.hit, wb.contrib, wb.pix_rng, wb.counts + bounce,
-                                                      wb.counts + bounce + 1, bounce);
-            else
-                k_shade<1><<<grid, kBlock, 0, L.st>>>(sc, fp, a, b, wb.hit, wb.contrib, wb.pix_rng, wb.counts + bounce,
-                                                      wb.counts + bounce + 1, bounce);
+#define RT_SHADE(M, B, O)                                                                                              \
+    k_shade<M, B, O><<<grid, kBlock, 0, L.st>>>(sc, fp, a, b, wb.hit, wb.contrib, wb.pix_rng, wb.counts + bounce,        \
+                                                wb.counts + bounce + 1, bounce)
+            const int variant = (L.rng_mode == RT_RNG_REF_PCG ? 0 : 4) | (L.shade_bin ? 2 : 0) | (L.shade_oct ? 1 : 0);
+            switch (variant) {
+                case 0: RT_SHADE(0, false, false); break;
+                case 1: RT_SHADE(0, false, true); break;
+                case 2: RT_SHADE(0, true, false); break;
+                case 3: RT_SHADE(0, true, true); break;
+                case 4: RT_SHADE(1, false, false); break;
+                case 5: RT_SHADE(1, false, true); break;
+                case 6: RT_SHADE(1, true, false); break;
+                default: RT_SHADE(1, true, true); break;
+            }
+#undef RT_SHADE
             (*L.kernel_launches)++;
         }
         PathArrays tmp = a;
@@ -1130,25 +1330,44 @@ cudaError_t wf_finalize(const Launcher& L, const uint32_t* frame_sum, uint8_t* o
     return cudaGetLastError();
 }
 
-cudaError_t wf_first_hit(const Launcher& L, const SceneView& sc, const FrameParams& fp, int mode, int32_t* tri_id,
-                         float* dst) {
+cudaError_t wf_first_hit(const Launcher& L, const SceneView& sc, const FrameParams& fp, int mode, const HookBuffers& hb,
+                         int32_t* tri_id, float* dst) {
     const long long n = (long long)fp.width * fp.height;
+    if (L.hooks_thread) {
+        if (L.rng_mode == RT_RNG_REF_PCG)
+            k_first_hit<0><<<nblocks(n), kBlock, 0, L.st>>>(sc, fp, mode, tri_id, dst);
+        else
+            k_first_hit<1><<<nblocks(n), kBlock, 0, L.st>>>(sc, fp, mode, tri_id, dst);
+        (*L.kernel_launches)++;
+        return cudaGetLastError();
+    }
     if (L.rng_mode == RT_RNG_REF_PCG)
-        k_first_hit<0><<<nblocks(n), kBlock, 0, L.st>>>(sc, fp, mode, tri_id, dst);
+        k_first_rays<0><<<nblocks(n), kBlock, 0, L.st>>>(fp, mode, hb.rays);
     else
-        k_first_hit<1><<<nblocks(n), kBlock, 0, L.st>>>(sc, fp, mode, tri_id, dst);
-    (*L.kernel_launches)++;
+        k_first_rays<1><<<nblocks(n), kBlock, 0, L.st>>>(fp, mode, hb.rays);
+    k_hook_count<<<1, 32, 0, L.st>>>(hb.counts, (uint32_t)n);
+    launch_extend(L, sc, hb.rays, hb.hit, hb.counts, hb.counts + 1, true, hb.stats);
+    k_unpack_hits<<<nblocks(n), kBlock, 0, L.st>>>(sc, hb.hit, n, tri_id, dst, nullptr, nullptr);
+    (*L.kernel_launches) += 3;
     return cudaGetLastError();
 }
 
 cudaError_t wf_trace_rays(const Launcher& L, const SceneView& sc, const float* o, const float* d, int64_t n,
-                          int32_t* tri, float* dst, float* bu, float* bv, unsigned long long* stats) {
+                          const HookBuffers& hb, int32_t* tri, float* dst, float* bu, float* bv) {
     if (n <= 0) return cudaSuccess;
-    if (L.instrument)
-        k_trace_rays<true><<<nblocks(n), kBlock, 0, L.st>>>(sc, o, d, n, tri, dst, bu, bv, stats);
-    else
-        k_trace_rays<false><<<nblocks(n), kBlock, 0, L.st>>>(sc, o, d, n, tri, dst, bu, bv, stats);
-    (*L.kernel_launches)++;
+    if (L.hooks_thread) {
+        if (L.instrument)
+            k_trace_rays<true><<<nblocks(n), kBlock, 0, L.st>>>(sc, o, d, n, tri, dst, bu, bv, hb.stats);
+        else
+            k_trace_rays<false><<<nblocks(n), kBlock, 0, L.st>>>(sc, o, d, n, tri, dst, bu, bv, hb.stats);
+        (*L.kernel_launches)++;
+        return cudaGetLastError();
+    }
+    k_pack_rays<<<nblocks(n), kBlock, 0, L.st>>>(o, d, n, hb.rays);
+    k_hook_count<<<1, 32, 0, L.st>>>(hb.counts, (uint32_t)n);
+    launch_extend(L, sc, hb.rays, hb.hit, hb.counts, hb.counts + 1, true, hb.stats);
+    k_unpack_hits<<<nblocks(n), kBlock, 0, L.st>>>(sc, hb.hit, n, tri, dst, bu, bv);
+    (*L.kernel_launches) += 3;
     return cudaGetLastError();
 }
 

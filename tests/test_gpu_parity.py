@@ -169,7 +169,7 @@ def test_bvh_is_valid(sphere_box):
     rlo, rhi = visit(0)
     assert seen.all()
     assert (rlo <= tlo.min(0)).all() and (rhi >= thi.max(0)).all()
-    assert be.counters()["bvh_depth"] < 128
+    assert be.counters()["bvh_depth"] < 256 and be.counters()["bvh_stack_need"] < 254
 
 
 @pytest.mark.parametrize("rng_mode", [rt.RNG_REF_PCG, rt.RNG_PHILOX])
@@ -476,7 +476,10 @@ def test_config4_scale_mesh_properties():
     assert scene.triangles.size == 14 + 2 * 2236 * 2236
     be = backend(scene)
     c = be.counters()
-    assert c["bvh_nodes"] == scene.triangles.size - 1 and c["bvh_depth"] < 128
+    # round 2: the exact worst-case stack of the wide tree is tracked by the builder (not 3 x depth), so the 10 M
+    # triangle scene walks the 4-wide nodes too
+    assert c["bvh_width"] == 4 and c["bvh_nodes"] < scene.triangles.size - 1 and c["bvh_stack_need"] < 254
+    assert c["build_ms"] < 60.0
     o, d = random_rays(200000, 21, -4.9, 4.9)
     tri, dst, _, _ = be.trace_rays(o, d)
     inside = np.linalg.norm(o - np.array([0, -1, 0], np.float32), axis=1) < 2.8   # inside the sphere: back faces culled
@@ -501,6 +504,22 @@ def test_config4_scale_mesh_properties():
     cam = rt.make_camera(96, 54, (0.0, 0.0, 15.5))
     u = rt.screenshot_uniforms(scene, cam, spp=2, max_bounce=8, env_light=False)
     total = be.screenshot_partial(u, 2)
+    # against the oracle at full size: its BVH (the reference builder's, BVH.h) answers a sample of rays and a 64x36
+    # first-hit map over the same 10 M triangles; ids and distances must be identical
+    orc = oracle.OracleScene.from_scene(scene)
+    oa, da = o[:5000], d[:5000]   # ~0.6 ms per ray on the CPU: the reference BVH ends in large leaves at its depth cap
+    ta, dsa, bua, bva = be.trace_rays(oa, da)
+    ot, od_, obu, obv = orc.trace_rays(oa, da, use_bvh=True)
+    assert np.array_equal(ta, ot) and np.array_equal(bits(dsa), bits(od_))
+    assert np.array_equal(bits(bua), bits(obu)) and np.array_equal(bits(bva), bits(obv))
+    cam_s = rt.make_camera(64, 36, (0.0, 0.0, 15.5))
+    us = rt.screenshot_uniforms(scene, cam_s, spp=1, max_bounce=8, env_light=False)
+    for mode in (rt.FIRST_HIT_CENTRE, rt.FIRST_HIT_SAMPLE0):
+        tri_m, dst_m = be.first_hit(us, mode)
+        otri_m, odst_m = orc.first_hit(us, mode, rng_mode=rt.RNG_PHILOX)
+        assert np.array_equal(tri_m, otri_m) and np.array_equal(bits(dst_m), bits(odst_m))
+    assert (tri_m >= 14).mean() > 0.2   # the sphere is in view
+    del orc
     be.close()
     acc = np.zeros_like(total)
     for rank in range(2):
@@ -576,6 +595,40 @@ def test_config1_full_size_screenshot_properties(classic):
     assert_image_equal(imgs[rt.RNG_PHILOX][y0:y1, x0:x1], ref[y0:y1, x0:x1, :3], "config 1 crop vs oracle")
 
 
+def test_real_asset_from_reference_loader():
+    """Config 2(i) with an asset that travels: RayTracing/Data/sleeping (372 triangles, a 512x512 texture, DIFFUSE /
+    SPECULAR / LIGHT / TEXTURE materials) as decoded by the reference's own loader (tests/golden/make_golden_assets.sh
+    -> sleeping.rtsc.gz, committed), inside addCornellBox and inside the mirror box: first-hit ids, frames and random
+    rays bit-identical to the oracle."""
+    import gzip, os, tempfile
+    src = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "sleeping.rtsc.gz")
+    with tempfile.TemporaryDirectory() as tmp:
+        path = os.path.join(tmp, "sleeping.rtsc")
+        with open(path, "wb") as f:
+            f.write(gzip.open(src, "rb").read())
+        for container in ("cornell", "mirror"):
+            scene = rt.scene_from_rtsc(path, container=container)
+            assert scene.triangles.size == 372 + 16 and len(scene.textures) == 1
+            orc = oracle.OracleScene.from_scene(scene)
+            be = backend(scene)
+            cam = rt.camera_for_box(scene, 128, 72)
+            u = rt.screenshot_uniforms(scene, cam, spp=4, max_bounce=10, env_light=False)
+            for mode in (rt.FIRST_HIT_CENTRE, rt.FIRST_HIT_SAMPLE0):
+                tri, dst = be.first_hit(u, mode)
+                otri, odst = orc.first_hit(u, mode, rng_mode=rt.RNG_PHILOX)
+                assert np.array_equal(tri, otri) and np.array_equal(bits(dst), bits(odst))
+            assert (tri >= 0).any() and len(np.unique(tri)) > 20
+            be.render_frame(u)
+            assert_image_equal(be.read_frame(), orc.render_frame(u, rng_mode=rt.RNG_PHILOX), f"sleeping in {container} box")
+            lo = scene.triangles["a"][:, :3].min(0)
+            hi = scene.triangles["a"][:, :3].max(0)
+            o, d = random_rays(20000, 5, float(lo.min()) * 0.9, float(hi.max()) * 0.9)
+            a = be.trace_rays(o, d)
+            b = orc.trace_rays(o, d, use_bvh=False)
+            assert np.array_equal(a[0], b[0]) and np.array_equal(bits(a[1]), bits(b[1]))
+            be.close()
+
+
 def test_real_asset_robot_if_generated():
     """Config 2(i): Data/robot (25 599 triangles, three textures incl. a 4096^2 one, loaded by the reference's
     own loader + stb into assets/_gen/robot.rtsc by tools/make_assets.sh) inside addCornellBox.  Skipped when the
@@ -600,3 +653,146 @@ def test_real_asset_robot_if_generated():
     a = be.trace_rays(o, d)
     b = orc.trace_rays(o, d, use_bvh=True)
     assert np.array_equal(a[0], b[0]) and np.array_equal(bits(a[1]), bits(b[1]))
+
+
+# ------------------------------------------------------------------------------------------------ round 2
+@pytest.mark.parametrize("env", [{"RT_SHADE_BIN": "0", "RT_SHADE_OCT": "0"}, {"RT_SHADE_BIN": "1", "RT_SHADE_OCT": "0"},
+                                 {"RT_SHADE_BIN": "0", "RT_SHADE_OCT": "1"}, {"RT_EXT_TOP": "1"}, {"RT_HOOKS": "thread"},
+                                 {"RT_BVH_WIDTH": "2"}, {"RT_MAX_PATHS_MI": "1"}])
+@pytest.mark.parametrize("rng_mode", [rt.RNG_REF_PCG, rt.RNG_PHILOX])
+def test_kernel_variants_change_no_bit(monkeypatch, env, rng_mode):
+    """Block-local material queues, octant-ordered output, the shared-memory top of the tree, the per-thread hooks,
+    the binary tree and a tiny path budget only reorder work: frame, first-hit map and random rays must equal the
+    oracle bit for bit under every switch (the defaults are covered by every other test)."""
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    zoo = scenes.material_zoo()
+    mir = rt.scene_textured_sphere(n_quads=20, container="mirror", tex_size=32)
+    cases = [(zoo, scenes.zoo_camera(80, 48), True, 9), (mir, rt.camera_for_box(mir, 72, 40), False, 12)]
+    for scene, cam, env_light, depth in cases:
+        orc = oracle.OracleScene.from_scene(scene)
+        u = rt.screenshot_uniforms(scene, cam, spp=5, max_bounce=depth, env_light=env_light)
+        be = backend(scene, rng_mode=rng_mode)
+        be.render_frame(u)
+        assert_image_equal(be.read_frame(), orc.render_frame(u, rng_mode=rng_mode), f"variant {env}")
+        tri, dst = be.first_hit(u, rt.FIRST_HIT_SAMPLE0)
+        otri, odst = orc.first_hit(u, rt.FIRST_HIT_SAMPLE0, rng_mode=rng_mode)
+        assert np.array_equal(tri, otri) and np.array_equal(bits(dst), bits(odst))
+        o, d = random_rays(5000, 3, -4.0, 4.0)
+        a = be.trace_rays(o, d)
+        b = orc.trace_rays(o, d, use_bvh=False)
+        assert np.array_equal(a[0], b[0]) and np.array_equal(bits(a[1]), bits(b[1]))
+        assert np.array_equal(bits(a[2]), bits(b[2])) and np.array_equal(bits(a[3]), bits(b[3]))
+        be.close()
+
+
+def test_camera_far_outside_the_scene_uses_the_widened_slabs(classic):
+    """rt_scene.cuh drops the relative widening of the slab test's far side when the camera stands within ~2 grid
+    extents of the scene; beyond that the widened variant must run.  Both must give the oracle's first-hit map."""
+    scene, orc = classic
+    for z in (15.5, 60.0, 4000.0):
+        cam = rt.make_camera(64, 64, (0.0, 0.0, z), hfov=0.5 * 10.0 / z)
+        u = rt.screenshot_uniforms(scene, cam, spp=2, max_bounce=4, env_light=False)
+        be = backend(scene)
+        be.render_frame(u)
+        assert_image_equal(be.read_frame(), orc.render_frame(u, rng_mode=rt.RNG_PHILOX), f"camera at z={z}")
+        tri, dst = be.first_hit(u, rt.FIRST_HIT_CENTRE)
+        otri, odst = orc.first_hit(u, rt.FIRST_HIT_CENTRE)
+        assert np.array_equal(tri, otri) and np.array_equal(bits(dst), bits(odst))
+        be.close()
+
+
+def test_config3_full_mesh_mirror_box():
+    """BASELINE config 3 with its real mesh size (100 352 triangles in the full-mirror box, depth 16): first-hit map,
+    random rays and a small frame against the oracle (round 1 only covered a 4.6 k-triangle mirror scene)."""
+    scene = rt.scene_textured_sphere(n_quads=224, container="mirror", tex_size=256)
+    orc = oracle.OracleScene.from_scene(scene)
+    be = backend(scene)
+    cam = rt.camera_for_box(scene, 96, 54)
+    u = rt.screenshot_uniforms(scene, cam, spp=2, max_bounce=16, env_light=False)
+    for mode in (rt.FIRST_HIT_CENTRE, rt.FIRST_HIT_SAMPLE0):
+        tri, dst = be.first_hit(u, mode)
+        otri, odst = orc.first_hit(u, mode, rng_mode=rt.RNG_PHILOX)
+        assert np.array_equal(tri, otri) and np.array_equal(bits(dst), bits(odst))
+    o, d = random_rays(20000, 9, -4.0, 4.0)
+    a = be.trace_rays(o, d)
+    b = orc.trace_rays(o, d, use_bvh=True)
+    assert np.array_equal(a[0], b[0]) and np.array_equal(bits(a[1]), bits(b[1]))
+    be.render_frame(u)
+    assert_image_equal(be.read_frame(), orc.render_frame(u, rng_mode=rt.RNG_PHILOX), "config 3 frame, full mesh")
+    be.close()
+
+
+def test_destroy_releases_device_memory(sphere_box):
+    """rt_destroy must give back every byte (round 1 leaked the 4-wide node array: 64 B per triangle per context)."""
+    import torch
+    scene, _ = sphere_box
+    big = rt.scene_textured_sphere(n_quads=224, container="cornell", tex_size=64)
+    cam = rt.camera_for_box(big, 64, 36)
+    u = rt.screenshot_uniforms(big, cam, spp=2, max_bounce=4, env_light=False)
+
+    def cycle():
+        be = backend(big)
+        be.render_frame(u)
+        be.first_hit(u)
+        be.close()
+
+    cycle()
+    torch.cuda.synchronize()
+    free0, _ = torch.cuda.mem_get_info(0)
+    for _ in range(8):
+        cycle()
+    torch.cuda.synchronize()
+    free1, _ = torch.cuda.mem_get_info(0)
+    assert free0 - free1 < (4 << 20), f"{(free0 - free1) / 2**20:.1f} MiB lost over 8 create/build/destroy cycles"
+
+
+def test_rejected_uploads_leave_a_consistent_scene(classic):
+    """A rejected rt_scene_set_triangles changes nothing; a material table that no longer covers a built scene is
+    refused; a non-finite vertex fails the build with RT_ERR_INVALID and the context stays usable."""
+    scene, orc = classic
+    be = backend(scene)
+    cam = rt.make_camera(48, 48, (0.0, 0.0, 15.5))
+    u = rt.screenshot_uniforms(scene, cam, spp=2, max_bounce=4, env_light=False)
+    be.render_frame(u)
+    good = be.read_frame()
+    bad = scene.triangles.copy()
+    bad["materialIndex"][3] = -7
+    with pytest.raises(rt.BackendError):
+        be.set_triangles(bad)
+    be.render_frame(u)                       # the previous scene is still there and still built
+    assert_image_equal(be.read_frame(), good, "scene after a rejected upload")
+    with pytest.raises(rt.BackendError):
+        be.set_materials(scene.materials[:3])  # the built scene references material 4 and 5
+    be.render_frame(u)
+    assert_image_equal(be.read_frame(), good, "scene after a rejected material table")
+    nf = scene.triangles.copy()
+    nf["b"][5, 1] = np.inf
+    be.set_triangles(nf)
+    with pytest.raises(rt.BackendError) as e:
+        be.build()
+    assert "non-finite" in str(e.value)
+    be.set_triangles(scene.triangles)        # not sticky: the same context builds and renders again
+    be.build()
+    be.render_frame(u)
+    assert_image_equal(be.read_frame(), good, "scene rebuilt after a failed build")
+    be.close()
+
+
+def test_duplicate_geometry_builds(classic):
+    """Runs of identical boxes (the reference inserts the sky-light plane twice, rayTracing.cpp:428-431) make the
+    agglomerative builder merge one pair per round; a few thousand copies must still build (single-block tail or the
+    Karras fallback) and resolve ties to the lowest index."""
+    scene, _ = classic
+    one = scene.triangles[:2].copy()
+    many = np.concatenate([one] * 1500 + [scene.triangles])
+    s = rt.Scene()
+    s.add_fixed_materials()
+    s.add_triangles(many)
+    be = backend(s)
+    orc = oracle.OracleScene.from_scene(s)
+    o, d = random_rays(3000, 13, -4.5, 4.5)
+    a = be.trace_rays(o, d)
+    b = orc.trace_rays(o, d, use_bvh=False)
+    assert np.array_equal(a[0], b[0]) and np.array_equal(bits(a[1]), bits(b[1]))
+    be.close()

@@ -305,3 +305,16 @@ def test_unorm8_reciprocal_sequence_is_exact():
         assert float(q) == float(np.float32(b) / np.float32(255.0))
         wrong_plain += q0 != rn32(x / 255)
     assert wrong_plain == 126
+
+
+def test_rejection_test_without_sqrt():
+    """k_shade evaluates the acceptance test of compute.glsl:180, `length(v) < 1`, as `dot(v, v) < 1` (no sqrt).
+    The two agree for every binary32 x = dot(v, v): sqrt is monotonic and correctly rounded, sqrt(x) >= 1 for
+    x >= 1, and for the largest x below 1 (1 - 2^-24) the exact root 1 - 2^-25 - 2^-51 - ... lies below the midpoint
+    of (1 - 2^-24, 1) and rounds down.  Checked here on every float within 2^16 ulp of 1 and on random ones."""
+    one = np.float32(1.0).view(np.uint32)
+    near = (np.arange(-65536, 65537, dtype=np.int64) + int(one)).astype(np.uint32).view(np.float32)
+    rng = np.random.default_rng(5)
+    rnd = rng.uniform(0.0, 3.0, 2_000_000).astype(np.float32)
+    for x in (near, rnd):
+        assert np.array_equal(np.sqrt(x, dtype=np.float32) < np.float32(1.0), x < np.float32(1.0))
