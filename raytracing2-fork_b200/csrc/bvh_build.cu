@@ -26,6 +26,9 @@
 //   k_emit_tris    sorted triangle records: (a, e0, e1, N, unit normal, material) | (uvs, material, orig)
 // Everything is deterministic (stable sort, min/max are order independent), so every GPU of a
 // multi-GPU job builds the identical tree.
+#include <cstdio>
+#include <cstdlib>
+
 #include "rt_internal.h"
 
 namespace rt {
@@ -389,6 +392,8 @@ __device__ __forceinline__ float union_area(float4 alo, float4 ahi, float4 blo, 
 // its cluster count while its last tile publishes the next one:
 //   ctl[4 * (round & 1) + 0] = m        clusters entering the round
 //   ctl[4 * (round & 1) + 1] = created  inner nodes created so far
+//   ctl[4 * (round & 1) + 2] = buf      which of the two cluster lists is current (a round that has nothing to
+//                                       do — the count is already small enough for the tail — moves no data)
 //   ctl[8]                   = ticket   tile ids of the look-back scan are handed out in arrival order
 // tileState[t] (uint64): bits 63..62 = 0 invalid / 1 tile aggregate / 2 inclusive prefix; bits 59..32 = kept
 // clusters, bits 31..0 = merged pairs.
@@ -448,17 +453,20 @@ __global__ void k_ploc_ctl_init(uint32_t* __restrict__ ctl, int n) {
 // nearest neighbour in the window; also re-arms the scan of this round (ticket, tile states)
 __global__ void __launch_bounds__(256) k_ploc_nn(int n, int round, uint32_t* __restrict__ ctl,
                                                  unsigned long long* __restrict__ tileState,
-                                                 const int32_t* __restrict__ cluster,
+                                                 const int32_t* __restrict__ cluster0,
+                                                 const int32_t* __restrict__ cluster1,
                                                  const float4* __restrict__ boxes, int32_t* __restrict__ nn) {
     const uint32_t* cin = ctl + 4 * (round & 1);
     uint32_t* cout = ctl + 4 * ((round + 1) & 1);
     const int m = (int)cin[0];
+    const int32_t* cluster = cin[2] ? cluster1 : cluster0;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i == 0) {
         ctl[kCtlTicket] = 0u;
         if (m <= kPlocTailMax) {  // nothing (more) to do globally: the round is a no-op, the state moves on unchanged
             cout[0] = cin[0];
             cout[1] = cin[1];
+            cout[2] = cin[2];
         }
     }
     if (m <= kPlocTailMax) return;
@@ -472,8 +480,7 @@ __global__ void __launch_bounds__(256) k_ploc_nn(int n, int round, uint32_t* __r
 // and the merge itself.  The last tile publishes the next round's cluster count.
 __global__ void __launch_bounds__(256) k_ploc_merge_scan(int n, int round, uint32_t* __restrict__ ctl,
                                                          unsigned long long* __restrict__ tileState,
-                                                         const int32_t* __restrict__ clusterIn,
-                                                         int32_t* __restrict__ clusterOut,
+                                                         int32_t* __restrict__ cluster0, int32_t* __restrict__ cluster1,
                                                          const int32_t* __restrict__ nn, float4* __restrict__ boxes,
                                                          int32_t* __restrict__ children, uint32_t* __restrict__ height,
                                                          int32_t* __restrict__ parentOf,
@@ -483,6 +490,9 @@ __global__ void __launch_bounds__(256) k_ploc_merge_scan(int n, int round, uint3
     uint32_t* cout = ctl + 4 * ((round + 1) & 1);
     const int m = (int)cin[0];
     const int created = (int)cin[1];
+    const uint32_t buf = cin[2];
+    const int32_t* clusterIn = buf ? cluster1 : cluster0;
+    int32_t* clusterOut = buf ? cluster0 : cluster1;
     if (m <= kPlocTailMax) return;
     __shared__ uint32_t sTile;
     __shared__ unsigned long long sWarp[8];
@@ -558,6 +568,7 @@ __global__ void __launch_bounds__(256) k_ploc_merge_scan(int n, int round, uint3
                 cout[0] = kept;
             }
             cout[1] = (uint32_t)created + merged;
+            cout[2] = buf ^ 1u;
             status[kBuildPlocRounds] = (uint32_t)round + 1u;
         }
     }
@@ -587,13 +598,15 @@ __global__ void __launch_bounds__(256) k_ploc_merge_scan(int n, int round, uint3
 // with the cluster list in shared memory.  Most ROUNDS of a build happen here — the cluster count falls
 // geometrically at first and then the large clusters absorb the stragglers one or two per round.
 __global__ void __launch_bounds__(1024) k_ploc_tail(int n, int round, uint32_t* __restrict__ ctl,
-                                                    const int32_t* __restrict__ clusterIn, float4* __restrict__ boxes,
+                                                    const int32_t* __restrict__ cluster0,
+                                                    const int32_t* __restrict__ cluster1, float4* __restrict__ boxes,
                                                     int32_t* __restrict__ children, uint32_t* __restrict__ height,
                                                     int32_t* __restrict__ parentOf, uint32_t* __restrict__ innerCount,
                                                     uint32_t* __restrict__ status) {
     uint32_t* cio = ctl + 4 * (round & 1);
     int m = (int)cio[0];
     int created = (int)cio[1];
+    const int32_t* clusterIn = cio[2] ? cluster1 : cluster0;
     if (m <= 1 || m > kPlocTailMax) return;
     __shared__ int32_t cl[2][kPlocTailMax];
     __shared__ int32_t snn[kPlocTailMax];
@@ -888,25 +901,37 @@ cudaError_t build_lbvh(const BuildArgs& a, cudaStream_t st, uint64_t* launches) 
     const int n = a.n;
     auto nb = [](long long count, int per) { return (int)((count + per - 1) / per); };
     uint64_t L = 0;
+    // RT_BUILD_DEBUG=1: synchronise after every launch and name the first kernel that fails
+    static const bool debug = getenv("RT_BUILD_DEBUG") != nullptr;
+#define RT_DBG()                                                                                            \
+    do {                                                                                                    \
+        if (debug) {                                                                                        \
+            cudaError_t de = cudaStreamSynchronize(st);                                                     \
+            if (de != cudaSuccess) {                                                                        \
+                fprintf(stderr, "build_lbvh: launch before line %d failed: %s\n", __LINE__, cudaGetErrorString(de)); \
+                return de;                                                                                  \
+            }                                                                                               \
+        }                                                                                                   \
+    } while (0)
     uint32_t* maxDepth = a.status + kBuildDepth;
     cudaMemsetAsync(a.status, 0, kBuildStatusWords * sizeof(uint32_t), st);
-    k_init_bounds<<<1, 32, 0, st>>>(a.bounds); L++;
-    k_tri_bounds<<<min(nb(n, 256), a.sm_count * 8), 256, 0, st>>>(a.tris, n, a.centroid, a.bounds, a.status); L++;
+    k_init_bounds<<<1, 32, 0, st>>>(a.bounds); L++; RT_DBG();
+    k_tri_bounds<<<min(nb(n, 256), a.sm_count * 8), 256, 0, st>>>(a.tris, n, a.centroid, a.bounds, a.status); L++; RT_DBG();
     if (n >= 2) {
-        k_morton<<<nb(n, 256), 256, 0, st>>>(a.centroid, n, a.bounds, a.keys[0], a.vals[0]); L++;
+        k_morton<<<nb(n, 256), 256, 0, st>>>(a.centroid, n, a.bounds, a.keys[0], a.vals[0]); L++; RT_DBG();
         const int nblocks = nb(n, kSortTile);
         int cur = 0;
         for (int pass = 0; pass < 8; pass++) {
             const int shift = pass * 8;
-            k_hist<<<nblocks, kSortThreads, 0, st>>>(a.keys[cur], n, shift, a.hist, nblocks); L++;
-            k_scan<<<1, 1024, 0, st>>>(a.hist, 256 * nblocks); L++;
+            k_hist<<<nblocks, kSortThreads, 0, st>>>(a.keys[cur], n, shift, a.hist, nblocks); L++; RT_DBG();
+            k_scan<<<1, 1024, 0, st>>>(a.hist, 256 * nblocks); L++; RT_DBG();
             k_scatter<<<nblocks, kSortThreads, 0, st>>>(a.keys[cur], a.vals[cur], a.keys[cur ^ 1],
-                                                        a.vals[cur ^ 1], n, shift, a.hist, nblocks); L++;
+                                                        a.vals[cur ^ 1], n, shift, a.hist, nblocks); L++; RT_DBG();
             cur ^= 1;
         }
         // 8 passes: the result is back in buffer 0
     } else {
-        k_iota<<<1, 32, 0, st>>>(a.vals[0], n); L++;
+        k_iota<<<1, 32, 0, st>>>(a.vals[0], n); L++; RT_DBG();
     }
     int32_t* order = nullptr;
     if (n >= 2 && a.use_ploc) {
@@ -918,8 +943,8 @@ cudaError_t build_lbvh(const BuildArgs& a, cudaStream_t st, uint64_t* launches) 
         uint32_t* innerCount = reinterpret_cast<uint32_t*>(a.centroid) + n;
         uint32_t* ctl = a.hist;                           // the histograms are dead after the sort
         unsigned long long* tileState = reinterpret_cast<unsigned long long*>(a.hist + kCtlWords);
-        k_ploc_init<<<nb(n, 256), 256, 0, st>>>(a.tris, a.vals[0], n, a.bounds, a.boxes, cluster[0], height); L++;
-        k_ploc_ctl_init<<<1, 32, 0, st>>>(ctl, n); L++;
+        k_ploc_init<<<nb(n, 256), 256, 0, st>>>(a.tris, a.vals[0], n, a.bounds, a.boxes, cluster[0], height); L++; RT_DBG();
+        k_ploc_ctl_init<<<1, 32, 0, st>>>(ctl, n); L++; RT_DBG();
         // Rounds are enqueued in chunks without the host knowing the cluster count (kernels read it from `ctl`;
         // grids are sized for the count at the start of the chunk, surplus blocks exit at once); after each chunk
         // the single-block tail gets a chance and the host reads back two words.
@@ -929,48 +954,48 @@ cudaError_t build_lbvh(const BuildArgs& a, cudaStream_t st, uint64_t* launches) 
         while (m > 1u) {
             if (m > (uint32_t)kPlocTailMax) {
                 for (int k = 0; k < chunk; k++, round++) {
-                    k_ploc_nn<<<nb(m, 256), 256, 0, st>>>(n, round, ctl, tileState, cluster[round & 1], a.boxes, nn); L++;
-                    k_ploc_merge_scan<<<nb(m, kPlocTile), 256, 0, st>>>(n, round, ctl, tileState, cluster[round & 1],
-                                                                         cluster[(round + 1) & 1], nn, a.boxes, a.children,
-                                                                         height, parentOf, innerCount, a.status); L++;
+                    k_ploc_nn<<<nb(m, 256), 256, 0, st>>>(n, round, ctl, tileState, cluster[0], cluster[1], a.boxes, nn); L++; RT_DBG();
+                    k_ploc_merge_scan<<<nb(m, kPlocTile), 256, 0, st>>>(n, round, ctl, tileState, cluster[0],
+                                                                         cluster[1], nn, a.boxes, a.children,
+                                                                         height, parentOf, innerCount, a.status); L++; RT_DBG();
                 }
                 chunk = min(chunk * 2, 64);
             }
-            k_ploc_tail<<<1, 1024, 0, st>>>(n, round, ctl, cluster[round & 1], a.boxes, a.children, height, parentOf,
-                                            innerCount, a.status); L++;
+            k_ploc_tail<<<1, 1024, 0, st>>>(n, round, ctl, cluster[0], cluster[1], a.boxes, a.children, height, parentOf,
+                                            innerCount, a.status); L++; RT_DBG();
             uint32_t state[2];
             cudaMemcpyAsync(state, ctl + 4 * (round & 1), sizeof state, cudaMemcpyDeviceToHost, st);
             cudaError_t e = cudaStreamSynchronize(st);
             if (e != cudaSuccess) return e;
             m = state[0];
             if (m > 1u && round >= kMaxGlobalRounds) {  // runs of identical boxes merge one pair per round: not worth waiting for
-                k_set_word<<<1, 32, 0, st>>>(a.status + kBuildPlocStuck, 1u); L++;
+                k_set_word<<<1, 32, 0, st>>>(a.status + kBuildPlocStuck, 1u); L++; RT_DBG();
                 m = 0u;
             }
         }
-        k_ploc_depth<<<1, 32, 0, st>>>(height, maxDepth); L++;
+        k_ploc_depth<<<1, 32, 0, st>>>(height, maxDepth); L++; RT_DBG();
         if (a.dfs_layout) {
             order = reinterpret_cast<int32_t*>(a.centroid) + 2 * (size_t)n;
-            k_dfs_order<<<nb(n - 1, 256), 256, 0, st>>>(n, a.children, parentOf, innerCount, order); L++;
+            k_dfs_order<<<nb(n - 1, 256), 256, 0, st>>>(n, a.children, parentOf, innerCount, order); L++; RT_DBG();
         }
     } else {
         if (n >= 2) {
-            k_hierarchy<<<nb(n - 1, 256), 256, 0, st>>>(a.keys[0], n, a.children, a.parent); L++;
+            k_hierarchy<<<nb(n - 1, 256), 256, 0, st>>>(a.keys[0], n, a.children, a.parent); L++; RT_DBG();
             cudaMemsetAsync(a.flags, 0, sizeof(uint32_t) * (size_t)(n - 1), st);
             cudaMemsetAsync(a.nodeDepth, 0, sizeof(uint32_t) * (size_t)(n - 1), st);
         }
         k_refit<<<nb(n, 256), 256, 0, st>>>(a.tris, a.vals[0], n, a.bounds, a.children, a.parent, a.boxes, a.flags,
-                                            a.nodeDepth, maxDepth); L++;
+                                            a.nodeDepth, maxDepth); L++; RT_DBG();
     }
-    k_grid<<<1, 32, 0, st>>>(a.bounds, a.grid); L++;
-    if (n >= 2) { k_emit_nodes<<<nb(n - 1, 256), 256, 0, st>>>(n, a.children, a.boxes, a.grid, order, a.nodes); L++; }
+    k_grid<<<1, 32, 0, st>>>(a.bounds, a.grid); L++; RT_DBG();
+    if (n >= 2) { k_emit_nodes<<<nb(n - 1, 256), 256, 0, st>>>(n, a.children, a.boxes, a.grid, order, a.nodes); L++; RT_DBG(); }
     if (n >= 2 && a.nodes4) {
         // queues in the two key buffers of the sort (n int2 each, dead by now); counters behind the PLOC control
         // block; per-node stack need in the height array (dead after k_ploc_depth / k_refit)
         int2* q[2] = {reinterpret_cast<int2*>(a.keys[0]), reinterpret_cast<int2*>(a.keys[1])};
         uint32_t* cnt = a.hist + 32;
         uint32_t* needOf = a.nodeDepth;
-        k_collapse_init<<<1, 32, 0, st>>>(q[0], cnt, a.wide_count, needOf); L++;
+        k_collapse_init<<<1, 32, 0, st>>>(q[0], cnt, a.wide_count, needOf); L++; RT_DBG();
         // levels are enqueued 16 at a time with grids sized by the bound min(4^level, n - 1) on the queue length;
         // an empty level is a no-op, and after each group the host reads one word to see whether work remains
         int level = 0;
@@ -980,7 +1005,7 @@ cudaError_t build_lbvh(const BuildArgs& a, cudaStream_t st, uint64_t* launches) 
                 const long long bound = level < 13 ? (1ll << (2 * level)) : (long long)n;
                 const long long cap = bound < (long long)(n - 1) ? bound : (long long)(n - 1);
                 k_collapse4<<<nb(cap, 256), 256, 0, st>>>(n, level, a.children, a.boxes, a.grid, q[level & 1],
-                                                          q[(level + 1) & 1], cnt, a.wide_count, needOf, a.nodes4); L++;
+                                                          q[(level + 1) & 1], cnt, a.wide_count, needOf, a.nodes4); L++; RT_DBG();
             }
             cudaMemcpyAsync(&pending, cnt + level % 3, sizeof(uint32_t), cudaMemcpyDeviceToHost, st);
             cudaError_t e = cudaStreamSynchronize(st);
@@ -992,8 +1017,9 @@ cudaError_t build_lbvh(const BuildArgs& a, cudaStream_t st, uint64_t* launches) 
         if (e != cudaSuccess) return e;
         if (a.wide_levels) *a.wide_levels = (int)levels;
     }
-    k_emit_tris<<<nb(n, 256), 256, 0, st>>>(a.tris, a.vals[0], n, a.geom, a.shade, a.orig); L++;
+    k_emit_tris<<<nb(n, 256), 256, 0, st>>>(a.tris, a.vals[0], n, a.geom, a.shade, a.orig); L++; RT_DBG();
     if (launches) *launches += L;
+#undef RT_DBG
     return cudaGetLastError();
 }
 

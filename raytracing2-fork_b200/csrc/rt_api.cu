@@ -113,7 +113,7 @@ struct rt_ctx {
     int node_steps_wide = 2, extend_blocks_per_sm_wide = 8;
     int use_ploc = 1, dfs_layout = 1, speculative = 1, shade_blocks_per_sm = 64;
     int top_smem = 0;              // RT_EXT_TOP=1: k_extend keeps the top four levels of the wide tree in shared memory
-    int shade_bin = 1, shade_oct = 1;  // k_shade: block-local material queues / octant-ordered block output
+    int force_widen = 0;           // RT_EXT_WIDEN=1: every launch uses the widened slab test (debugging aid)
     int hooks_thread = 0;          // RT_HOOKS=thread: parity hooks walk the binary tree per thread (preview's code path)
     int extend_blocks_per_sm_top = 8;
     int bvh_width = 4;             // 4: k_extend walks 4-wide nodes collapsed from the binary tree; 2: the binary tree (RT_BVH_WIDTH)
@@ -223,10 +223,10 @@ Launcher make_launcher(rt_ctx* ctx, const rt_uniforms* u = nullptr) {
     Launcher L;
     L.st = ctx->stream;
     L.top_smem = ctx->top_smem != 0;
-    L.widen_primary = u ? widen_needed(ctx, *u) : true;
+    L.widen_primary = (u && !ctx->force_widen) ? widen_needed(ctx, *u) : true;
+    L.widen_always = ctx->force_widen != 0;
     L.hooks_thread = ctx->hooks_thread != 0;
-    L.shade_bin = ctx->shade_bin != 0;
-    L.shade_oct = ctx->shade_oct != 0;
+
     L.sm_count = ctx->sm_count;
     L.rng_mode = ctx->cfg.rng_mode;
     L.instrument = ctx->cfg.instrument != 0;
@@ -423,6 +423,7 @@ FrameParams make_params(rt_ctx* ctx, const rt_uniforms& u) {
     fp.frames_in_batch = 1;
     fp.samples_in_batch = 1;
     fp.frame_stride = 1;
+    fp.debug_zero_contrib = getenv("RT_DEBUG_ZERO_CONTRIB") ? 1 : 0;
     return fp;
 }
 
@@ -610,8 +611,7 @@ int rt_create(rt_ctx** out, const rt_config* cfg) {
     if (const char* e3 = getenv("RT_EXT_BLOCKS_PER_SM"))
         ctx->extend_blocks_per_sm = ctx->extend_blocks_per_sm_wide = ctx->extend_blocks_per_sm_top = std::max(1, std::min(32, atoi(e3)));
     if (const char* e11 = getenv("RT_EXT_TOP")) ctx->top_smem = atoi(e11);
-    if (const char* e12 = getenv("RT_SHADE_BIN")) ctx->shade_bin = atoi(e12);
-    if (const char* e13 = getenv("RT_SHADE_OCT")) ctx->shade_oct = atoi(e13);
+    if (const char* e15 = getenv("RT_EXT_WIDEN")) ctx->force_widen = atoi(e15);
     if (const char* e14 = getenv("RT_HOOKS")) ctx->hooks_thread = strcmp(e14, "thread") == 0;
     if (const char* e10 = getenv("RT_EXT_NODE_STEPS_WIDE")) ctx->node_steps_wide = std::max(1, std::min(4, atoi(e10)));
     if (ctx->d_stats.reserve(4 * sizeof(unsigned long long)) != cudaSuccess ||

@@ -87,6 +87,7 @@ struct FrameParams {
     int32_t frames_in_batch;    // >= 1
     int32_t samples_in_batch;   // samples of one pixel of one frame in flight together (1 in RT_RNG_REF_PCG mode)
     int32_t frame_stride;       // frameIndex step between batch frames (world_size under RT_SPLIT_FRAMES)
+    int32_t debug_zero_contrib; // RT_DEBUG_ZERO_CONTRIB=1: raygen clears every contrib slot (debugging aid)
     const int32_t* rows;        // local row -> absolute row (RT_SPLIT_TILES), NULL = identity
     FastDiv div_pixels;         // / local_pixels
     FastDiv div_samples;        // / samples_in_batch
@@ -127,10 +128,9 @@ struct Launcher {
     int node_steps;    // k_extend: node steps per vote
     bool speculative;  // k_extend: postponed-leaf variant
     bool top_smem;     // k_extend (4-wide): root + three levels of the tree staged in shared memory
+    bool widen_always;   // debugging aid: widened slab test on every bounce
     bool widen_primary;  // camera rays may start far outside the quantisation grid (rt_scene.cuh, slab1)
     bool hooks_thread; // parity hooks walk the binary tree per thread instead of running k_extend
-    bool shade_bin;    // k_shade: block-local material queues
-    bool shade_oct;    // k_shade: block-aggregated, octant-ordered output
     int shade_blocks_per_sm;  // grid-stride k_shade: blocks per SM
     uint64_t* kernel_launches;
     uint64_t* extend_launches;

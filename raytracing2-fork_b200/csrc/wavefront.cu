@@ -250,7 +250,7 @@ __global__ void __launch_bounds__(kBlock) k_raygen(const __grid_constant__ Frame
     cur.misc[i] = make_float4(1.0f, __int_as_float(i), __uint_as_float(rng.carry()), __int_as_float(0));
     // every path writes its slot of `contrib` exactly once, at its terminal event in k_shade (the bounce limit is
     // one); only a frame without any bounce needs the zero
-    if (fp.u.maxBounceCount <= 0) contrib[i] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    if (fp.u.maxBounceCount <= 0 || fp.debug_zero_contrib) contrib[i] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
 }
 
 // ---------------------------------------------------------------------------------------------- k_extend
@@ -670,96 +670,28 @@ __device__ __forceinline__ BounceRandoms bounce_randoms(Rng<1>& rng, bool needDi
 }
 
 // ---------------------------------------------------------------------------------------------- k_shade
-// Block-local queues.  The material switch of S:499-541 diverges per lane (ncu, round 1: 17.6 of 32 lanes per
-// instruction in k_shade), so every block first sorts the 256 paths of its window by MATERIAL CLASS — ballots and
-// popcounts per warp, one prefix over the (warp, class) counts — and thread t then shades the t-th path of that
-// order: warps are (nearly) homogeneous in the switch, in the texture fetch and in whether they need random numbers at
-// all (terminal paths: miss, light, unknown material).  The queue lives in shared memory and costs no HBM traffic: the
-// sorted loads stay inside the block's 4 KB windows of the path arrays.
-// The survivors leave the block the same way: ordered by the OCTANT of their new direction and appended to the next
-// queue with ONE atomicAdd per block, so that the warps of the next k_extend launch receive rays that start close
-// together (same block of the previous queue) and walk the tree in the same near / far order.
-enum { kClsTerminal = 0, kClsDiffuse = 1, kClsTexture = 2, kClsSpecular = 3, kClsGlass = 4, kClsInvalid = 5, kNumCls = 6 };
-__device__ __forceinline__ int material_class(int32_t type) {
-    switch (type) {
-        case RT_MAT_DIFFUSE:
-        case RT_MAT_CHECKER: return kClsDiffuse;
-        case RT_MAT_TEXTURE: return kClsTexture;
-        case RT_MAT_SPECULAR: return kClsSpecular;
-        case RT_MAT_GLASS: return kClsGlass;
-        default: return kClsTerminal;  // LIGHT, GLASS_HIGHLIGHT and unknown types end the path (S:515-520,539-540)
-    }
-}
-template <int NB>
-struct BlockBins {
-    uint32_t cnt[kBlock / 32][NB];  // per (warp, bin): count, then the exclusive prefix over the warps
-    uint32_t tot[NB];
-};
-// Position of this thread in the block's stable counting sort by `key` (0 <= key < NB).  Two block barriers;
-// s.tot holds the bin totals afterwards.
-template <int NB>
-__device__ __forceinline__ uint32_t block_sort_pos(int key, BlockBins<NB>& s) {
-    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-    uint32_t mine = 0u;
-#pragma unroll
-    for (int b = 0; b < NB; b++) {
-        const uint32_t m = __ballot_sync(0xffffffffu, key == b);
-        if (key == b) mine = m;
-        if ((int)lane == b) s.cnt[warp][b] = (uint32_t)__popc(m);
-    }
-    const uint32_t below = (uint32_t)__popc(mine & ((1u << lane) - 1u));
-    __syncthreads();
-    if (threadIdx.x < NB) {
-        uint32_t run = 0u;
-#pragma unroll
-        for (int w = 0; w < kBlock / 32; w++) {
-            const uint32_t c = s.cnt[w][threadIdx.x];
-            s.cnt[w][threadIdx.x] = run;
-            run += c;
-        }
-        s.tot[threadIdx.x] = run;
-    }
-    __syncthreads();
-    uint32_t base = 0u;
-#pragma unroll
-    for (int b = 0; b < NB; b++) base += (b < key) ? s.tot[b] : 0u;
-    return base + s.cnt[warp][key] + below;
-}
-
+// Not split per material.  Round 2 built block-local material queues (every block sorted the 256 paths of its window
+// by material class with warp ballots + a prefix over the (warp, class) counts, and appended its survivors ordered by
+// the octant of their new direction with one atomicAdd per block) and measured them on config 2, B200, same run:
+// plain kernel 4995 Mrays/s; class queues 4762 (-4.7 %); octant-ordered block output 4803 (-3.8 %, k_extend unchanged
+// at 7.93 ms per launch: ray octants at block granularity buy no coherence); both 4632 (-7.3 %) — raw lines in
+// profiles/r2_shade_queues_ab.txt, code in commit c59b9e8.  The sort's barriers and its uncoalesced (sorted) loads cost
+// more than the divergence they remove: DIFFUSE and TEXTURE share the switch case, so on this workload only the
+// texture fetch diverges.  What is kept from that work: the random numbers of a bounce are drawn by the converged
+// warp, and a warp whose paths all end (miss, light, unknown material) draws none.
 // One bounce of S:481-560 for every live path.  `bounce` is the 0-based index of this segment.
-// BIN: block-local material queues; OCT: block-aggregated, octant-ordered output (both change only the order in which
-// paths are processed and stored, never a value: every path's arithmetic is the same, the image is independent of it).
-template <int MODE, bool BIN, bool OCT>
+template <int MODE>
 __global__ void __launch_bounds__(kBlock, 4) k_shade(const __grid_constant__ SceneView sc,
                                                   const __grid_constant__ FrameParams fp, PathArrays cur,
                                                   PathArrays next, const float4* __restrict__ hit,
                                                   float4* __restrict__ contrib, uint32_t* __restrict__ pix_rng,
                                                   const uint32_t* __restrict__ countIn,
                                                   uint32_t* __restrict__ countOut, int bounce) {
-    __shared__ BlockBins<kNumCls> sBin;
-    __shared__ BlockBins<9> sOct;
-    __shared__ uint16_t sOrder[kBlock];
-    __shared__ uint32_t sBase;
     const uint32_t n = *countIn;
     const uint32_t lane = threadIdx.x & 31u;
     constexpr uint32_t FULL = 0xffffffffu;
     for (uint32_t base = blockIdx.x * kBlock; base < n; base += gridDim.x * kBlock) {
-        uint32_t i = base + threadIdx.x;
-        if (BIN) {
-            int cls = kClsInvalid;
-            if (i < n) {
-                const int32_t hs = __float_as_int(__ldg(&hit[i].w));
-                cls = kClsTerminal;
-                if (hs >= 0) {
-                    const int32_t mi = __float_as_int(__ldg(&sc.tri_geom[4 * hs + 3].w));
-                    cls = material_class(__float_as_int(__ldg(&sc.materials[6 * mi + 4].z)));
-                }
-            }
-            const uint32_t pos = block_sort_pos<kNumCls>(cls, sBin);
-            sOrder[pos] = (uint16_t)threadIdx.x;
-            __syncthreads();
-            i = base + sOrder[threadIdx.x];  // threads beyond the live count sort last and keep an index >= n
-        }
+        const uint32_t i = base + threadIdx.x;
         const bool valid = i < n;
         bool alive = false;
         V3 o = v3(0, 0, 0), d = v3(0, 0, 1), rayColor = v3(0, 0, 0);
@@ -888,36 +820,21 @@ __global__ void __launch_bounds__(kBlock, 4) k_shade(const __grid_constant__ Sce
                 flags = (uint32_t)bounceCount | ((insideGlass ? 1u : 0u) << 16);
             }
         }
-        // compaction: survivors take consecutive places in the next queue
-        uint32_t pos = 0u;
-        if (OCT) {
-            const int key = alive ? ((d.x < 0.0f ? 1 : 0) | (d.y < 0.0f ? 2 : 0) | (d.z < 0.0f ? 4 : 0)) : 8;
-            pos = block_sort_pos<9>(key, sOct);
-            if (threadIdx.x == 0) {
-                uint32_t total = 0u;
-#pragma unroll
-                for (int b = 0; b < 8; b++) total += sOct.tot[b];
-                sBase = total ? atomicAdd(countOut, total) : 0u;
-            }
-            __syncthreads();
-            pos += sBase;
-        } else {
-            const uint32_t mask = __ballot_sync(FULL, alive);
-            uint32_t basePos = 0;
-            if (mask) {
-                const int leader = __ffs(mask) - 1;
-                if ((int)lane == leader) basePos = atomicAdd(countOut, (uint32_t)__popc(mask));
-                basePos = __shfl_sync(FULL, basePos, leader);
-            }
-            pos = basePos + __popc(mask & ((1u << lane) - 1u));
+        // compaction: the survivors of this warp take consecutive places in the next queue
+        const uint32_t mask = __ballot_sync(FULL, alive);
+        uint32_t basePos = 0;
+        if (mask) {
+            const int leader = __ffs(mask) - 1;
+            if ((int)lane == leader) basePos = atomicAdd(countOut, (uint32_t)__popc(mask));
+            basePos = __shfl_sync(FULL, basePos, leader);
         }
+        const uint32_t pos = basePos + __popc(mask & ((1u << lane) - 1u));
         if (alive) {
             next.od0[pos] = make_float4(o.x, o.y, o.z, d.x);
             next.od1[pos] = make_float4(d.y, d.z, rayColor.x, rayColor.y);
             next.misc[pos] = make_float4(rayColor.z, __int_as_float(slotId), __uint_as_float(carry),
                                          __uint_as_float(flags));
         }
-        if (BIN || OCT) __syncthreads();  // the shared queues are rewritten by the next window
     }
 }
 
@@ -1276,25 +1193,16 @@ cudaError_t wf_render_batch(const Launcher& L, const SceneView& sc, const WaveBu
         {
             Timed t(L, 0);
             // camera rays may start far outside the scene; every later segment starts on a surface of it
-            launch_extend(L, sc, a, wb.hit, wb.counts + bounce, cursors + bounce, bounce == 0 ? L.widen_primary : false, wb.stats);
+            launch_extend(L, sc, a, wb.hit, wb.counts + bounce, cursors + bounce, bounce == 0 ? L.widen_primary : L.widen_always, wb.stats);
         }
         {
             Timed t(L, 1);
-#define RT_SHADE(M, B, O)                                                                                              \
-    k_shade<M, B, O><<<grid, kBlock, 0, L.st>>>(sc, fp, a, b, wb.hit, wb.contrib, wb.pix_rng, wb.counts + bounce,        \
-                                                wb.counts + bounce + 1, bounce)
-            const int variant = (L.rng_mode == RT_RNG_REF_PCG ? 0 : 4) | (L.shade_bin ? 2 : 0) | (L.shade_oct ? 1 : 0);
-            switch (variant) {
-                case 0: RT_SHADE(0, false, false); break;
-                case 1: RT_SHADE(0, false, true); break;
-                case 2: RT_SHADE(0, true, false); break;
-                case 3: RT_SHADE(0, true, true); break;
-                case 4: RT_SHADE(1, false, false); break;
-                case 5: RT_SHADE(1, false, true); break;
-                case 6: RT_SHADE(1, true, false); break;
-                default: RT_SHADE(1, true, true); break;
-            }
-#undef RT_SHADE
+            if (L.rng_mode == RT_RNG_REF_PCG)
+                k_shade<0><<<grid, kBlock, 0, L.st>>>(sc, fp, a, b, wb.hit, wb.contrib, wb.pix_rng, wb.counts + bounce,
+                                                      wb.counts + bounce + 1, bounce);
+            else
+                k_shade<1><<<grid, kBlock, 0, L.st>>>(sc, fp, a, b, wb.hit, wb.contrib, wb.pix_rng, wb.counts + bounce,
+                                                      wb.counts + bounce + 1, bounce);
             (*L.kernel_launches)++;
         }
         PathArrays tmp = a;

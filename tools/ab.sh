@@ -1,0 +1,16 @@
+#!/bin/sh
+# A/B of kernel switches on BASELINE config 2 (1080p, 4 frames): one bench line per environment, value only.
+# usage: tools/ab.sh "NAME=VAL NAME=VAL" "NAME=VAL" ...   ("" = defaults)
+for envs in "$@"; do
+  out=$(env $envs python bench.py --workload config2 --steps 3 --warmup 2 --no-cpu --no-side --no-microbench 2>&1 | tail -1)
+  python - "$envs" "$out" <<'PY'
+import json, sys
+try:
+    d = json.loads(sys.argv[2])
+    r = d["roofline"]
+    print(f"[{sys.argv[1] or 'default'}] {d['value']:.0f} Mrays/s  {d['ms_per_step']:.1f} ms/step  extend {r['t_measured_ms']:.2f} ms/launch  "
+          f"share {r['extend_share_of_step']:.3f}  crc {d['checksum']} gate {d['parity_gate'].get('screenshot')}")
+except Exception as e:
+    print(f"[{sys.argv[1]}] FAILED: {sys.argv[2][-400:]}")
+PY
+done

@@ -1,0 +1,45 @@
+#!/usr/bin/env python
+"""Summarise an ncu report (--page raw --csv) into the metrics DESIGN.md / profiles/ quote.
+usage: tools/ncu_summary.py report.ncu-rep [more.ncu-rep ...]"""
+import csv, io, subprocess, sys
+
+KEYS = [
+    "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
+    "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "lts__t_sector_hit_rate.pct", "l1tex__t_sector_hit_rate.pct",
+    "lts__t_bytes.sum", "l1tex__t_bytes.sum", "lts__throughput.avg.pct_of_peak_sustained_elapsed",
+    "sm__warps_active.avg.pct_of_peak_sustained_active", "launch__registers_per_thread", "launch__grid_size", "launch__block_size",
+    "launch__occupancy_limit_registers", "launch__occupancy_limit_shared_mem", "smsp__inst_executed.sum",
+    "smsp__thread_inst_executed_per_inst_executed.ratio", "smsp__issue_active.avg.pct_of_peak_sustained_active",
+    "l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed",
+    "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active",
+    "sm__inst_executed_pipe_fmaheavy.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_fmalite.avg.pct_of_peak_sustained_active",
+    "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active",
+    "sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_active", "sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active",
+    "sm__pipe_xu_cycles_active.avg.pct_of_peak_sustained_active",
+    "smsp__warps_eligible.avg.per_cycle_active", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
+]
+STALLS = "smsp__average_warps_issue_stalled_"
+
+for rep in sys.argv[1:]:
+    out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(io.StringIO(out)))
+    hdr, units, data = rows[0], rows[1], rows[2:]
+    col = {h: i for i, h in enumerate(hdr)}
+    print(f"# {rep}")
+    names = [r[col["Kernel Name"]].split("(")[0][-28:] for r in data]
+    print("| metric | unit | " + " | ".join(f"{i}:{n}" for i, n in enumerate(names)) + " |")
+    print("|---|---|" + "---|" * len(data))
+    for k in KEYS:
+        if k in col:
+            print(f"| {k} | {units[col[k]]} | " + " | ".join(r[col[k]] for r in data) + " |")
+    for i, r in enumerate(data):
+        st = []
+        for h in hdr:
+            if h.startswith(STALLS) and h.endswith("_per_warp_active.pct"):
+                try:
+                    st.append((float(r[col[h]]), h[len(STALLS):-len("_per_warp_active.pct")]))
+                except ValueError:
+                    pass
+        st.sort(reverse=True)
+        print(f"stalls launch {i} ({names[i]}): " + ", ".join(f"{n} {v:.1f}%" for v, n in st[:8]))
+    print()
