@@ -353,7 +353,7 @@ __global__ void __launch_bounds__(256) k_refit(const rt_triangle* __restrict__ t
 }
 
 // --------------------------------------------------------------------------------------------- PLOC
-constexpr int kPlocRadius = 10;
+constexpr int kPlocRadiusDefault = 10;  // search window of the clustering (RT_PLOC_RADIUS overrides, 1..64)
 
 // leaf boxes in Morton order (entity n-1+slot), cluster list = all leaves
 __global__ void __launch_bounds__(256) k_ploc_init(const rt_triangle* __restrict__ tris,
@@ -373,8 +373,10 @@ __global__ void __launch_bounds__(256) k_ploc_init(const rt_triangle* __restrict
         lo[k] = fminf(fminf(t.a[k], t.b[k]), t.c[k]) - pad;
         hi[k] = fmaxf(fmaxf(t.a[k], t.b[k]), t.c[k]) + pad;
     }
-    boxes[2 * (n - 1 + s)] = make_float4(lo[0], lo[1], lo[2], 0.0f);
-    boxes[2 * (n - 1 + s) + 1] = make_float4(hi[0], hi[1], hi[2], 0.0f);
+    // .w of the lower corner = SAH cost of the subtree given that its box is hit (one triangle test = 1),
+    // .w of the upper corner = triangles it holds AS A LEAF (0 = inner node that stays split)
+    boxes[2 * (n - 1 + s)] = make_float4(lo[0], lo[1], lo[2], 1.0f);
+    boxes[2 * (n - 1 + s) + 1] = make_float4(hi[0], hi[1], hi[2], __int_as_float(1));
     cluster[s] = ~s;
     height[n - 1 + s] = 0u;
 }
@@ -403,13 +405,13 @@ constexpr int kCtlTicket = 8;
 constexpr int kCtlWords = 16;
 constexpr unsigned long long kTileAgg = 1ull << 62, kTileIncl = 2ull << 62, kTileFlagMask = 3ull << 62;
 
-__device__ __forceinline__ int ploc_nearest(const int32_t* __restrict__ cluster, int i, int m, int n,
-                                            const float4* __restrict__ boxes) {
+// (no __restrict__ here: k_ploc_tail reads boxes that the same kernel wrote in its previous round)
+__device__ __forceinline__ int ploc_nearest(const int32_t* cluster, int i, int m, int n, const float4* boxes, int radius) {
     const int ei = entity_of(cluster[i], n);
     const float4 lo = boxes[2 * ei], hi = boxes[2 * ei + 1];
     float best = 3.4e38f;
     int bj = -1;
-    const int j0 = max(0, i - kPlocRadius), j1 = min(m - 1, i + kPlocRadius);
+    const int j0 = max(0, i - radius), j1 = min(m - 1, i + radius);
     for (int j = j0; j <= j1; j++) {
         if (j == i) continue;
         const int ej = entity_of(cluster[j], n);
@@ -427,20 +429,47 @@ __device__ __forceinline__ int ploc_nearest(const int32_t* __restrict__ cluster,
     return bj;
 }
 
+// Leaves of more than one triangle.  The two triangles of a quad have almost the same box, so a tree with one
+// triangle per leaf makes every ray that touches the quad test two boxes, push and pop one of them, and visit two
+// leaves (ncu, round 2: the leaf phase of k_extend was 22 % of its warp instructions at ~9 active lanes, 4.25
+// triangle tests per segment).  At every merge the builder compares, bottom-up, the SAH cost of keeping the node
+// split, 2 Cb + (A_a cost_a + A_b cost_b) / A, with the cost of one leaf holding all its triangles, count x 1, and
+// marks the node as a leaf when that is cheaper and the count allowed.  Cb = cost of a box test relative to a
+// triangle test, maxTris = 1 switches the feature off.
+struct LeafPolicy {
+    float cb;
+    int maxTris;
+};
+__device__ __forceinline__ float box_area(float4 lo, float4 hi) {
+    const float dx = hi.x - lo.x, dy = hi.y - lo.y, dz = hi.z - lo.z;
+    return dx * dy + dy * dz + dz * dx;
+}
 // one merge: node `id` = union of clusters a and b
 __device__ __forceinline__ void ploc_make_node(int id, int32_t a, int32_t b, int n, float4* __restrict__ boxes,
                                                int32_t* __restrict__ children, uint32_t* __restrict__ height,
-                                               int32_t* __restrict__ parentOf, uint32_t* __restrict__ innerCount) {
+                                               int32_t* __restrict__ parentOf, uint32_t* __restrict__ innerCount,
+                                               int32_t* __restrict__ leafParent, LeafPolicy pol) {
     const int ea = entity_of(a, n), eb = entity_of(b, n);
     const float4 alo = boxes[2 * ea], ahi = boxes[2 * ea + 1], blo = boxes[2 * eb], bhi = boxes[2 * eb + 1];
-    boxes[2 * id] = make_float4(fminf(alo.x, blo.x), fminf(alo.y, blo.y), fminf(alo.z, blo.z), 0.0f);
-    boxes[2 * id + 1] = make_float4(fmaxf(ahi.x, bhi.x), fmaxf(ahi.y, bhi.y), fmaxf(ahi.z, bhi.z), 0.0f);
+    float4 lo = make_float4(fminf(alo.x, blo.x), fminf(alo.y, blo.y), fminf(alo.z, blo.z), 0.0f);
+    float4 hi = make_float4(fmaxf(ahi.x, bhi.x), fmaxf(ahi.y, bhi.y), fmaxf(ahi.z, bhi.z), 0.0f);
+    const int la = __float_as_int(ahi.w), lb = __float_as_int(bhi.w);
+    const float area = box_area(lo, hi);
+    const float split = 2.0f * pol.cb + (area > 0.0f ? (box_area(alo, ahi) * alo.w + box_area(blo, bhi) * blo.w) / area
+                                                     : alo.w + blo.w);
+    const float leaf = (float)(la + lb);
+    // the root (id 0, the last node created) always stays an inner node: the traversal starts at an inner node
+    const bool asLeaf = id != 0 && la > 0 && lb > 0 && la + lb <= pol.maxTris && leaf <= split;
+    lo.w = asLeaf ? leaf : split;
+    hi.w = __int_as_float(asLeaf ? la + lb : 0);
+    boxes[2 * id] = lo;
+    boxes[2 * id + 1] = hi;
     children[2 * id] = a;
     children[2 * id + 1] = b;
     height[id] = max(height[ea], height[eb]) + 1u;
     // bookkeeping for the depth-first relabelling: parent links and inner nodes per subtree
-    if (a >= 0) parentOf[a] = id;
-    if (b >= 0) parentOf[b] = id;
+    if (a >= 0) parentOf[a] = id; else leafParent[~a] = id;
+    if (b >= 0) parentOf[b] = id; else leafParent[~b] = id;
     innerCount[id] = 1u + (a >= 0 ? innerCount[a] : 0u) + (b >= 0 ? innerCount[b] : 0u);
 }
 
@@ -455,7 +484,7 @@ __global__ void __launch_bounds__(256) k_ploc_nn(int n, int round, uint32_t* __r
                                                  unsigned long long* __restrict__ tileState,
                                                  const int32_t* __restrict__ cluster0,
                                                  const int32_t* __restrict__ cluster1,
-                                                 const float4* __restrict__ boxes, int32_t* __restrict__ nn) {
+                                                 const float4* __restrict__ boxes, int32_t* __restrict__ nn, int radius) {
     const uint32_t* cin = ctl + 4 * (round & 1);
     uint32_t* cout = ctl + 4 * ((round + 1) & 1);
     const int m = (int)cin[0];
@@ -472,7 +501,7 @@ __global__ void __launch_bounds__(256) k_ploc_nn(int n, int round, uint32_t* __r
     if (m <= kPlocTailMax) return;
     if (i < (m + kPlocTile - 1) / kPlocTile) tileState[i] = 0ull;
     if (i >= m) return;
-    nn[i] = ploc_nearest(cluster, i, m, n, boxes);
+    nn[i] = ploc_nearest(cluster, i, m, n, boxes, radius);
 }
 
 // Flags (mutual pair -> the lower position creates a node, the upper one disappears), exclusive prefix sums of
@@ -485,6 +514,7 @@ __global__ void __launch_bounds__(256) k_ploc_merge_scan(int n, int round, uint3
                                                          int32_t* __restrict__ children, uint32_t* __restrict__ height,
                                                          int32_t* __restrict__ parentOf,
                                                          uint32_t* __restrict__ innerCount,
+                                                         int32_t* __restrict__ leafParent, LeafPolicy pol,
                                                          uint32_t* __restrict__ status) {
     const uint32_t* cin = ctl + 4 * (round & 1);
     uint32_t* cout = ctl + 4 * ((round + 1) & 1);
@@ -584,7 +614,7 @@ __global__ void __launch_bounds__(256) k_ploc_merge_scan(int n, int round, uint3
             int32_t out = c[k];
             if (mutual[k]) {
                 const int id = firstId - (int)(uint32_t)(run & 0xffffffffu);
-                ploc_make_node(id, c[k], clusterIn[j[k]], n, boxes, children, height, parentOf, innerCount);
+                ploc_make_node(id, c[k], clusterIn[j[k]], n, boxes, children, height, parentOf, innerCount, leafParent, pol);
                 out = id;
                 run += 1ull;
             }
@@ -602,7 +632,8 @@ __global__ void __launch_bounds__(1024) k_ploc_tail(int n, int round, uint32_t* 
                                                     const int32_t* __restrict__ cluster1, float4* __restrict__ boxes,
                                                     int32_t* __restrict__ children, uint32_t* __restrict__ height,
                                                     int32_t* __restrict__ parentOf, uint32_t* __restrict__ innerCount,
-                                                    uint32_t* __restrict__ status) {
+                                                    int32_t* __restrict__ leafParent, LeafPolicy pol,
+                                                    uint32_t* __restrict__ status, int radius) {
     uint32_t* cio = ctl + 4 * (round & 1);
     int m = (int)cio[0];
     int created = (int)cio[1];
@@ -619,7 +650,7 @@ __global__ void __launch_bounds__(1024) k_ploc_tail(int n, int round, uint32_t* 
     uint32_t rounds = (uint32_t)round;
     bool stuck = false;
     while (m > 1) {
-        for (int i = t; i < m; i += 1024) snn[i] = ploc_nearest(cl[cur], i, m, n, boxes);
+        for (int i = t; i < m; i += 1024) snn[i] = ploc_nearest(cl[cur], i, m, n, boxes, radius);
         __syncthreads();
         // items 2t, 2t+1; packed sums: kept << 16 | merged (both <= 2048)
         uint32_t mine = 0u;
@@ -667,7 +698,7 @@ __global__ void __launch_bounds__(1024) k_ploc_tail(int n, int round, uint32_t* 
                 int32_t out = cl[cur][i];
                 if (mutual[k]) {
                     const int id = firstId - (int)(run & 0xffffu);
-                    ploc_make_node(id, out, cl[cur][j[k]], n, boxes, children, height, parentOf, innerCount);
+                    ploc_make_node(id, out, cl[cur][j[k]], n, boxes, children, height, parentOf, innerCount, leafParent, pol);
                     out = id;
                     run += 1u;
                 }
@@ -697,19 +728,44 @@ __global__ void __launch_bounds__(1024) k_ploc_tail(int n, int round, uint32_t* 
 // contiguous in memory.
 __global__ void __launch_bounds__(256) k_dfs_order(int n, const int32_t* __restrict__ children,
                                                    const int32_t* __restrict__ parentOf,
-                                                   const uint32_t* __restrict__ innerCount, int32_t* __restrict__ order) {
+                                                   const uint32_t* __restrict__ innerCount, int32_t* __restrict__ order,
+                                                   int32_t* __restrict__ firstTri) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n - 1) return;
-    uint32_t pos = 0;
+    uint32_t pos = 0, tris = 0;
     int node = i;
     while (node != 0) {
         const int p = parentOf[node];
         const int32_t left = children[2 * p];
         pos += 1u;
-        if (left != node && left >= 0) pos += innerCount[left];
+        if (left != node) {  // we hang on the right: the whole left sibling comes first
+            if (left >= 0) pos += innerCount[left];
+            tris += left >= 0 ? innerCount[left] + 1u : 1u;  // a binary subtree has one leaf more than inner nodes
+        }
         node = p;
     }
     order[i] = (int32_t)pos;
+    firstTri[i] = (int32_t)tris;  // triangles stored in front of this subtree's
+}
+// The same walk from every triangle: its place in the depth-first order of the leaves.  Triangle records are stored
+// in this order, so that the triangles of any subtree — in particular of a multi-triangle leaf — are contiguous.
+__global__ void __launch_bounds__(256) k_tri_order(int n, const int32_t* __restrict__ children,
+                                                   const int32_t* __restrict__ parentOf,
+                                                   const int32_t* __restrict__ leafParent,
+                                                   const uint32_t* __restrict__ innerCount, int32_t* __restrict__ triPos) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n) return;
+    uint32_t tris = 0;
+    int32_t me = ~s;
+    int p = leafParent[s];
+    for (;;) {
+        const int32_t left = children[2 * p];
+        if (left != me) tris += left >= 0 ? innerCount[left] + 1u : 1u;
+        if (p == 0) break;
+        me = p;
+        p = parentOf[p];
+    }
+    triPos[s] = (int32_t)tris;
 }
 
 __global__ void k_ploc_depth(const uint32_t* __restrict__ height, uint32_t* __restrict__ maxDepth) {
@@ -729,10 +785,27 @@ __global__ void k_grid(const uint32_t* __restrict__ bounds, float* __restrict__ 
     grid[3 + k] = 65535.0f / fmaxf(hi - lo, 1e-30f);
 }
 
+// How a child of the build tree appears in the emitted nodes: a triangle (c < 0) or an inner node marked as a leaf
+// becomes a packed leaf reference (first triangle record, count); any other inner node is returned as is (>= 0).
+// triPos / firstTri are NULL for the Karras tree: one triangle per leaf, records in Morton order.
+struct LeafView {
+    const float4* boxes;
+    const int32_t* triPos;
+    const int32_t* firstTri;
+    int n;
+    __device__ __forceinline__ bool is_leaf(int32_t c) const {
+        return c < 0 || (firstTri != nullptr && __float_as_int(boxes[2 * c + 1].w) > 0);
+    }
+    __device__ __forceinline__ int32_t leaf_code(int32_t c) const {
+        if (c < 0) return pack_leaf(triPos ? triPos[~c] : ~c, 1);
+        return pack_leaf(firstTri[c], __float_as_int(boxes[2 * c + 1].w));
+    }
+};
+
 __global__ void __launch_bounds__(256) k_emit_nodes(int n, const int32_t* __restrict__ children,
                                                     const float4* __restrict__ boxes,
                                                     const float* __restrict__ grid, const int32_t* __restrict__ order,
-                                                    uint4* __restrict__ nodes) {
+                                                    LeafView lv, uint4* __restrict__ nodes) {
     const int src = blockIdx.x * blockDim.x + threadIdx.x;
     if (src >= n - 1) return;
     const int32_t cl = children[2 * src], cr = children[2 * src + 1];
@@ -741,8 +814,8 @@ __global__ void __launch_bounds__(256) k_emit_nodes(int n, const int32_t* __rest
     const float4 rlo = boxes[2 * er], rhi = boxes[2 * er + 1];
     // `order` (optional) relabels inner nodes; the root keeps index 0
     const int i = order ? order[src] : src;
-    const int32_t pl = cl >= 0 ? (order ? order[cl] : cl) : pack_leaf(~cl, 1);
-    const int32_t pr = cr >= 0 ? (order ? order[cr] : cr) : pack_leaf(~cr, 1);
+    const int32_t pl = lv.is_leaf(cl) ? lv.leaf_code(cl) : (order ? order[cl] : cl);
+    const int32_t pr = lv.is_leaf(cr) ? lv.leaf_code(cr) : (order ? order[cr] : cr);
     // outward rounding with a guard band (kGuardCells) against the rounding of the scaling itself and of the slab test
     auto qlo = [&](float v, int k) {
         const float c = floorf((v - grid[k]) * grid[3 + k] - kGuardCells);
@@ -752,13 +825,18 @@ __global__ void __launch_bounds__(256) k_emit_nodes(int n, const int32_t* __rest
         const float c = ceilf((v - grid[k]) * grid[3 + k] + kGuardCells);
         return (uint32_t)fminf(fmaxf(c, 0.0f), 65535.0f);
     };
+    // one word per axis: lower plane | extent << 16 (rt_scene.cuh, slab1)
+    auto pack = [&](float lo, float hi, int k) {
+        const uint32_t l = qlo(lo, k), h = qhi(hi, k);
+        return l | ((h - l) << 16);
+    };
     uint4 a, b;
-    a.x = qlo(llo.x, 0) | (qhi(lhi.x, 0) << 16);
-    a.y = qlo(llo.y, 1) | (qhi(lhi.y, 1) << 16);
-    a.z = qlo(llo.z, 2) | (qhi(lhi.z, 2) << 16);
-    a.w = qlo(rlo.x, 0) | (qhi(rhi.x, 0) << 16);
-    b.x = qlo(rlo.y, 1) | (qhi(rhi.y, 1) << 16);
-    b.y = qlo(rlo.z, 2) | (qhi(rhi.z, 2) << 16);
+    a.x = pack(llo.x, lhi.x, 0);
+    a.y = pack(llo.y, lhi.y, 1);
+    a.z = pack(llo.z, lhi.z, 2);
+    a.w = pack(rlo.x, rhi.x, 0);
+    b.x = pack(rlo.y, rhi.y, 1);
+    b.y = pack(rlo.z, rhi.z, 2);
     b.z = (uint32_t)pl;
     b.w = (uint32_t)pr;
     nodes[2 * i + 0] = a;
@@ -769,9 +847,9 @@ __global__ void __launch_bounds__(256) k_emit_nodes(int n, const int32_t* __rest
 // 4-wide nodes, collapsed from the binary tree level by level: every queue entry (binary inner node, wide index)
 // starts from the node's two children and opens, at most twice, the inner child with the largest surface area.
 // Inner slots get a wide index and go to the next level's queue; leaf slots keep their packed leaf code; unused
-// slots carry the degenerate box at the far grid corner and the leaf code of triangle 0 (the slab test orders each
-// plane pair itself, so no box is unhittable; a ray through that corner merely tests one triangle more).
-// 64 bytes per node = 4 x (3 words of lo | hi << 16) + 4 children.
+// slots carry the degenerate box at the far grid corner and the leaf code of triangle 0 (no box is unhittable; a ray
+// through that corner merely tests one triangle more).
+// 64 bytes per node = 4 x (3 words of lo | extent << 16) + 4 children.
 // Numbering depends on atomics (topology does not), which is harmless: the closest-hit rule makes the image
 // independent of the hierarchy's layout.
 // Counters (uint32, in the dead histogram buffer): cnt[0..2] = queue sizes, rotating (level L reads cnt[L % 3],
@@ -783,7 +861,8 @@ __global__ void __launch_bounds__(256) k_collapse4(int n, int level, const int32
                                                    const float4* __restrict__ boxes, const float* __restrict__ grid,
                                                    const int2* __restrict__ qin, int2* __restrict__ qout,
                                                    uint32_t* __restrict__ cnt, uint32_t* __restrict__ wide,
-                                                   uint32_t* __restrict__ needOf, uint4* __restrict__ nodes4) {
+                                                   uint32_t* __restrict__ needOf, LeafView lv,
+                                                   uint4* __restrict__ nodes4) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t count = cnt[level % 3];
     uint32_t* qoutCount = cnt + (level + 1) % 3;
@@ -805,7 +884,7 @@ __global__ void __launch_bounds__(256) k_collapse4(int n, int level, const int32
         int best = -1;
         float bestA = -1.0f;
         for (int k = 0; k < cnt4; k++)
-            if (slot[k] >= 0) {
+            if (!lv.is_leaf(slot[k])) {
                 const float a = area(slot[k]);
                 if (a > bestA) { bestA = a; best = k; }
             }
@@ -828,20 +907,21 @@ __global__ void __launch_bounds__(256) k_collapse4(int n, int level, const int32
     for (int k = 0; k < 4; k++) {
         if (k < cnt4) {
             const float4 lo = boxes[2 * ent(slot[k])], hi = boxes[2 * ent(slot[k]) + 1];
-            w[3 * k + 0] = qlo(lo.x, 0) | (qhi(hi.x, 0) << 16);
-            w[3 * k + 1] = qlo(lo.y, 1) | (qhi(hi.y, 1) << 16);
-            w[3 * k + 2] = qlo(lo.z, 2) | (qhi(hi.z, 2) << 16);
+            const uint32_t lx = qlo(lo.x, 0), ly = qlo(lo.y, 1), lz = qlo(lo.z, 2);
+            w[3 * k + 0] = lx | ((qhi(hi.x, 0) - lx) << 16);  // lower plane | extent << 16 (rt_scene.cuh, slab1)
+            w[3 * k + 1] = ly | ((qhi(hi.y, 1) - ly) << 16);
+            w[3 * k + 2] = lz | ((qhi(hi.z, 2) - lz) << 16);
             int32_t ref;
-            if (slot[k] >= 0) {
+            if (!lv.is_leaf(slot[k])) {
                 ref = (int32_t)atomicAdd(&wide[0], 1u);
                 needOf[ref] = need;
                 qout[atomicAdd(qoutCount, 1u)] = make_int2(slot[k], ref);
             } else {
-                ref = pack_leaf(~slot[k], 1);
+                ref = lv.leaf_code(slot[k]);
             }
             w[12 + k] = (uint32_t)ref;
         } else {
-            w[3 * k + 0] = w[3 * k + 1] = w[3 * k + 2] = 0xffffffffu;  // lo = hi = 65535
+            w[3 * k + 0] = w[3 * k + 1] = w[3 * k + 2] = 0x0000ffffu;  // lo = 65535, extent 0
             w[12 + k] = (uint32_t)pack_leaf(0, 1);
         }
     }
@@ -870,12 +950,14 @@ __global__ void k_set_word(uint32_t* p, uint32_t v) {
 // Sorted triangle records.  e0, e1 and N are computed with exactly the operations of
 // compute.glsl:307-309 (and -fmad=false), so precomputing them changes no bit of any hit.
 __global__ void __launch_bounds__(256) k_emit_tris(const rt_triangle* __restrict__ tris,
-                                                   const uint32_t* __restrict__ sortedIdx, int n,
+                                                   const uint32_t* __restrict__ sortedIdx,
+                                                   const int32_t* __restrict__ triPos, int n,
                                                    float4* __restrict__ geom, float4* __restrict__ shade,
                                                    int32_t* __restrict__ orig) {
-    const int s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= n) return;
-    const uint32_t src = sortedIdx[s];
+    const int m = blockIdx.x * blockDim.x + threadIdx.x;  // position in Morton order
+    if (m >= n) return;
+    const uint32_t src = sortedIdx[m];
+    const int s = triPos ? triPos[m] : m;                  // record slot: depth-first order of the leaves
     const rt_triangle& t = tris[src];
     const V3 a = v3(t.a), b = v3(t.b), c = v3(t.c);
     const V3 e0 = b - a, e1 = c - a;
@@ -934,6 +1016,7 @@ cudaError_t build_lbvh(const BuildArgs& a, cudaStream_t st, uint64_t* launches) 
         k_iota<<<1, 32, 0, st>>>(a.vals[0], n); L++; RT_DBG();
     }
     int32_t* order = nullptr;
+    int32_t *firstTri = nullptr, *triPos = nullptr;
     if (n >= 2 && a.use_ploc) {
         // scratch: the sort's second key/value buffers are free now
         int32_t* cluster[2] = {reinterpret_cast<int32_t*>(a.vals[1]), a.parent};
@@ -941,6 +1024,9 @@ cudaError_t build_lbvh(const BuildArgs& a, cudaStream_t st, uint64_t* launches) 
         uint32_t* height = a.nodeDepth;                   // 2n - 1 entries
         int32_t* parentOf = reinterpret_cast<int32_t*>(a.centroid);     // centroids are dead after k_morton: 16n bytes
         uint32_t* innerCount = reinterpret_cast<uint32_t*>(a.centroid) + n;
+        int32_t* leafParent = reinterpret_cast<int32_t*>(a.flags);      // n + 1 words, free since the scan moved into the merge kernel
+        const LeafPolicy pol{a.leaf_cb > 0.0f ? a.leaf_cb : 0.35f, a.leaf_max_tris >= 1 ? (a.leaf_max_tris < 8 ? a.leaf_max_tris : 8) : 4};
+        const int radius = a.ploc_radius > 0 ? (a.ploc_radius < 64 ? a.ploc_radius : 64) : kPlocRadiusDefault;
         uint32_t* ctl = a.hist;                           // the histograms are dead after the sort
         unsigned long long* tileState = reinterpret_cast<unsigned long long*>(a.hist + kCtlWords);
         k_ploc_init<<<nb(n, 256), 256, 0, st>>>(a.tris, a.vals[0], n, a.bounds, a.boxes, cluster[0], height); L++; RT_DBG();
@@ -954,15 +1040,15 @@ cudaError_t build_lbvh(const BuildArgs& a, cudaStream_t st, uint64_t* launches) 
         while (m > 1u) {
             if (m > (uint32_t)kPlocTailMax) {
                 for (int k = 0; k < chunk; k++, round++) {
-                    k_ploc_nn<<<nb(m, 256), 256, 0, st>>>(n, round, ctl, tileState, cluster[0], cluster[1], a.boxes, nn); L++; RT_DBG();
+                    k_ploc_nn<<<nb(m, 256), 256, 0, st>>>(n, round, ctl, tileState, cluster[0], cluster[1], a.boxes, nn, radius); L++; RT_DBG();
                     k_ploc_merge_scan<<<nb(m, kPlocTile), 256, 0, st>>>(n, round, ctl, tileState, cluster[0],
                                                                          cluster[1], nn, a.boxes, a.children,
-                                                                         height, parentOf, innerCount, a.status); L++; RT_DBG();
+                                                                         height, parentOf, innerCount, leafParent, pol, a.status); L++; RT_DBG();
                 }
                 chunk = min(chunk * 2, 64);
             }
             k_ploc_tail<<<1, 1024, 0, st>>>(n, round, ctl, cluster[0], cluster[1], a.boxes, a.children, height, parentOf,
-                                            innerCount, a.status); L++; RT_DBG();
+                                            innerCount, leafParent, pol, a.status, radius); L++; RT_DBG();
             uint32_t state[2];
             cudaMemcpyAsync(state, ctl + 4 * (round & 1), sizeof state, cudaMemcpyDeviceToHost, st);
             cudaError_t e = cudaStreamSynchronize(st);
@@ -974,10 +1060,14 @@ cudaError_t build_lbvh(const BuildArgs& a, cudaStream_t st, uint64_t* launches) 
             }
         }
         k_ploc_depth<<<1, 32, 0, st>>>(height, maxDepth); L++; RT_DBG();
-        if (a.dfs_layout) {
-            order = reinterpret_cast<int32_t*>(a.centroid) + 2 * (size_t)n;
-            k_dfs_order<<<nb(n - 1, 256), 256, 0, st>>>(n, a.children, parentOf, innerCount, order); L++; RT_DBG();
-        }
+        // depth-first positions: of the inner nodes (their index in memory when dfs_layout is on), of the triangles in
+        // front of every subtree, and of every triangle (the order of the triangle records: leaves are contiguous runs)
+        int32_t* dfs = reinterpret_cast<int32_t*>(a.centroid) + 2 * (size_t)n;
+        firstTri = reinterpret_cast<int32_t*>(a.centroid) + 3 * (size_t)n;
+        triPos = reinterpret_cast<int32_t*>(a.vals[1]);  // the cluster list that lived here is dead
+        k_dfs_order<<<nb(n - 1, 256), 256, 0, st>>>(n, a.children, parentOf, innerCount, dfs, firstTri); L++; RT_DBG();
+        k_tri_order<<<nb(n, 256), 256, 0, st>>>(n, a.children, parentOf, leafParent, innerCount, triPos); L++; RT_DBG();
+        if (a.dfs_layout) order = dfs;
     } else {
         if (n >= 2) {
             k_hierarchy<<<nb(n - 1, 256), 256, 0, st>>>(a.keys[0], n, a.children, a.parent); L++; RT_DBG();
@@ -988,7 +1078,8 @@ cudaError_t build_lbvh(const BuildArgs& a, cudaStream_t st, uint64_t* launches) 
                                             a.nodeDepth, maxDepth); L++; RT_DBG();
     }
     k_grid<<<1, 32, 0, st>>>(a.bounds, a.grid); L++; RT_DBG();
-    if (n >= 2) { k_emit_nodes<<<nb(n - 1, 256), 256, 0, st>>>(n, a.children, a.boxes, a.grid, order, a.nodes); L++; RT_DBG(); }
+    const LeafView lv{a.boxes, triPos, firstTri, n};
+    if (n >= 2) { k_emit_nodes<<<nb(n - 1, 256), 256, 0, st>>>(n, a.children, a.boxes, a.grid, order, lv, a.nodes); L++; RT_DBG(); }
     if (n >= 2 && a.nodes4) {
         // queues in the two key buffers of the sort (n int2 each, dead by now); counters behind the PLOC control
         // block; per-node stack need in the height array (dead after k_ploc_depth / k_refit)
@@ -1005,7 +1096,7 @@ cudaError_t build_lbvh(const BuildArgs& a, cudaStream_t st, uint64_t* launches) 
                 const long long bound = level < 13 ? (1ll << (2 * level)) : (long long)n;
                 const long long cap = bound < (long long)(n - 1) ? bound : (long long)(n - 1);
                 k_collapse4<<<nb(cap, 256), 256, 0, st>>>(n, level, a.children, a.boxes, a.grid, q[level & 1],
-                                                          q[(level + 1) & 1], cnt, a.wide_count, needOf, a.nodes4); L++; RT_DBG();
+                                                          q[(level + 1) & 1], cnt, a.wide_count, needOf, lv, a.nodes4); L++; RT_DBG();
             }
             cudaMemcpyAsync(&pending, cnt + level % 3, sizeof(uint32_t), cudaMemcpyDeviceToHost, st);
             cudaError_t e = cudaStreamSynchronize(st);
@@ -1017,7 +1108,7 @@ cudaError_t build_lbvh(const BuildArgs& a, cudaStream_t st, uint64_t* launches) 
         if (e != cudaSuccess) return e;
         if (a.wide_levels) *a.wide_levels = (int)levels;
     }
-    k_emit_tris<<<nb(n, 256), 256, 0, st>>>(a.tris, a.vals[0], n, a.geom, a.shade, a.orig); L++; RT_DBG();
+    k_emit_tris<<<nb(n, 256), 256, 0, st>>>(a.tris, a.vals[0], triPos, n, a.geom, a.shade, a.orig); L++; RT_DBG();
     if (launches) *launches += L;
 #undef RT_DBG
     return cudaGetLastError();

@@ -113,6 +113,9 @@ struct rt_ctx {
     int node_steps_wide = 2, extend_blocks_per_sm_wide = 8;
     int use_ploc = 1, dfs_layout = 1, speculative = 1, shade_blocks_per_sm = 64;
     int top_smem = 0;              // RT_EXT_TOP=1: k_extend keeps the top four levels of the wide tree in shared memory
+    int leaf_max_tris = 0;         // RT_LEAF_MAX: most triangles per leaf (0 = builder default)
+    float leaf_cb = 0.0f;          // RT_LEAF_CB: SAH cost of a box test relative to a triangle test (0 = builder default)
+    int ploc_radius = 0;           // RT_PLOC_RADIUS: search window of the clustering (0 = the builder's default)
     int force_widen = 0;           // RT_EXT_WIDEN=1: every launch uses the widened slab test (debugging aid)
     int hooks_thread = 0;          // RT_HOOKS=thread: parity hooks walk the binary tree per thread (preview's code path)
     int extend_blocks_per_sm_top = 8;
@@ -612,6 +615,9 @@ int rt_create(rt_ctx** out, const rt_config* cfg) {
         ctx->extend_blocks_per_sm = ctx->extend_blocks_per_sm_wide = ctx->extend_blocks_per_sm_top = std::max(1, std::min(32, atoi(e3)));
     if (const char* e11 = getenv("RT_EXT_TOP")) ctx->top_smem = atoi(e11);
     if (const char* e15 = getenv("RT_EXT_WIDEN")) ctx->force_widen = atoi(e15);
+    if (const char* e17 = getenv("RT_LEAF_MAX")) ctx->leaf_max_tris = std::max(0, std::min(8, atoi(e17)));
+    if (const char* e18 = getenv("RT_LEAF_CB")) ctx->leaf_cb = (float)atof(e18);
+    if (const char* e16 = getenv("RT_PLOC_RADIUS")) ctx->ploc_radius = std::max(0, std::min(64, atoi(e16)));
     if (const char* e14 = getenv("RT_HOOKS")) ctx->hooks_thread = strcmp(e14, "thread") == 0;
     if (const char* e10 = getenv("RT_EXT_NODE_STEPS_WIDE")) ctx->node_steps_wide = std::max(1, std::min(4, atoi(e10)));
     if (ctx->d_stats.reserve(4 * sizeof(unsigned long long)) != cudaSuccess ||
@@ -759,6 +765,9 @@ int rt_scene_build(rt_ctx* ctx) {
     a.n = n;
     a.use_ploc = ctx->use_ploc;
     a.dfs_layout = ctx->dfs_layout;
+    a.ploc_radius = ctx->ploc_radius;
+    a.leaf_max_tris = ctx->leaf_max_tris;
+    a.leaf_cb = ctx->leaf_cb;
     a.centroid = ctx->d_centroid.as<float4>();
     a.bounds = ctx->d_bounds.as<uint32_t>();
     for (int i = 0; i < 2; i++) {
@@ -983,12 +992,14 @@ int rt_scene_get_bvh(rt_ctx* ctx, rt_bvh_node* nodes, int64_t* node_count, int32
         for (int64_t i = 0; i < nn; i++) {
             const uint4 a = raw[(size_t)i * 2], b = raw[(size_t)i * 2 + 1];
             rt_bvh_node& o = nodes[i];
-            o.lo_x[0] = deq(a.x & 0xffffu, 0); o.hi_x[0] = deq(a.x >> 16, 0);
-            o.lo_y[0] = deq(a.y & 0xffffu, 1); o.hi_y[0] = deq(a.y >> 16, 1);
-            o.lo_z[0] = deq(a.z & 0xffffu, 2); o.hi_z[0] = deq(a.z >> 16, 2);
-            o.lo_x[1] = deq(a.w & 0xffffu, 0); o.hi_x[1] = deq(a.w >> 16, 0);
-            o.lo_y[1] = deq(b.x & 0xffffu, 1); o.hi_y[1] = deq(b.x >> 16, 1);
-            o.lo_z[1] = deq(b.y & 0xffffu, 2); o.hi_z[1] = deq(b.y >> 16, 2);
+            // one word per axis: lower plane | extent << 16
+            auto hiq = [](uint32_t w) { return (w & 0xffffu) + (w >> 16); };
+            o.lo_x[0] = deq(a.x & 0xffffu, 0); o.hi_x[0] = deq(hiq(a.x), 0);
+            o.lo_y[0] = deq(a.y & 0xffffu, 1); o.hi_y[0] = deq(hiq(a.y), 1);
+            o.lo_z[0] = deq(a.z & 0xffffu, 2); o.hi_z[0] = deq(hiq(a.z), 2);
+            o.lo_x[1] = deq(a.w & 0xffffu, 0); o.hi_x[1] = deq(hiq(a.w), 0);
+            o.lo_y[1] = deq(b.x & 0xffffu, 1); o.hi_y[1] = deq(hiq(b.x), 1);
+            o.lo_z[1] = deq(b.y & 0xffffu, 2); o.hi_z[1] = deq(hiq(b.y), 2);
             const int32_t c[2] = {(int32_t)b.z, (int32_t)b.w};
             for (int k = 0; k < 2; k++) {
                 if (c[k] >= 0) {

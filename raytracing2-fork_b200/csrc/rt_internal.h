@@ -14,6 +14,9 @@ struct BuildArgs {
     int n;
     int use_ploc;             // 1 = PLOC hierarchy (default), 0 = Karras LBVH
     int dfs_layout;           // 1 = store PLOC nodes in depth-first order
+    int ploc_radius;          // search window of the clustering, 0 = default
+    int leaf_max_tris;        // most triangles a leaf may hold (PLOC; 0 = default 4, 1 = one triangle per leaf)
+    float leaf_cb;            // SAH cost of a box test relative to a triangle test (0 = default)
     float4* centroid;         // n
     uint32_t* bounds;         // 12 order-preserving uints
     uint64_t* keys[2];        // n each

@@ -6,8 +6,10 @@
 //   nodes    : 32 B per inner node = ONE 256-bit load (LDG.E.256 on sm_100a).  Both child boxes
 //              live in the parent, quantised to 16 bits per plane on a global grid over the padded
 //              scene box and rounded OUTWARD (the boxes only prune, so a larger box is always
-//              safe; triangle tests stay exact binary32):
-//                w0..w2 = left  child (lo.x | hi.x << 16, lo.y | hi.y << 16, lo.z | hi.z << 16)
+//              safe; triangle tests stay exact binary32).  Per axis one word = lower plane | EXTENT << 16
+//              (extent = upper - lower plane, in cells): the slab test then needs no min / max to order the
+//              two planes of an axis (slab1 below):
+//                w0..w2 = left  child (lo.x | ext.x << 16, lo.y | ext.y << 16, lo.z | ext.z << 16)
 //                w3..w5 = right child, w6 = left, w7 = right
 //              child >= 0: inner node index; child < 0: leaf, ~child = first | (count-1) << 27.
 //              (The reference re-reads the 48-byte parent and then two 48-byte children per visit:
@@ -48,18 +50,11 @@ struct HitRec {
     int32_t slot;  // sorted slot, -1 = miss
 };
 
-#ifndef RT_SLAB_FMA
-#define RT_SLAB_FMA 1
-#endif
 // traversal stack entries per ray: 16 in shared memory (k_extend), the rest in local memory.  rt_scene_build checks the
 // exact worst case of the tree it built against this (binary: depth; 4-wide: sum of children-1 along the deepest path).
 constexpr int kStackSize = 256;
-// outward rounding margin of the quantised planes, in grid cells (bvh_build.cu k_emit_nodes)
-#if RT_SLAB_FMA
-constexpr float kGuardCells = 0.0625f;
-#else
-constexpr float kGuardCells = 1e-3f;
-#endif
+// outward rounding margin of the quantised planes, in grid cells (bvh_build.cu k_emit_nodes; bound in slab1 below)
+constexpr float kGuardCells = 0.125f;
 
 // 256-bit read-only global load (sm_100a: LDG.E.ENL2.256.CONSTANT): one instruction, one L1TEX
 // wavefront per lane for 32 bytes, where four 128-bit loads of a 64-byte record would cost four.
@@ -83,12 +78,9 @@ __device__ __forceinline__ float q_hi(uint32_t w) { return __uint_as_float(0x4B0
 
 // The ray in grid coordinates: per-axis scaling of origin and direction leaves t unchanged.
 struct GridRay {
-#if RT_SLAB_FMA
     float ox, oy, oz;     // -(o - grid_lo) * grid_inv * i: the constant term of t = q * i + c
-#else
-    float ox, oy, oz;     // (o - grid_lo) * grid_inv
-#endif
-    float ix, iy, iz;     // 1 / (d * grid_inv), clamped to +-1e28 (RT_SLAB_FMA=0: a zero component gives +-inf)
+    float ix, iy, iz;     // 1 / (d * grid_inv), clamped to +-1e28
+    float nx, ny, nz;     // min(i, 0): the slope that takes the lower plane's t to the NEAR plane's
 };
 __device__ __forceinline__ GridRay make_grid_ray(const SceneView& sc, V3 o, V3 d) {
     GridRay g;
@@ -98,7 +90,6 @@ __device__ __forceinline__ GridRay make_grid_ray(const SceneView& sc, V3 o, V3 d
     g.ix = 1.0f / (d.x * sc.grid_inv[0]);
     g.iy = 1.0f / (d.y * sc.grid_inv[1]);
     g.iz = 1.0f / (d.z * sc.grid_inv[2]);
-#if RT_SLAB_FMA
     // finite slopes keep q*i + c free of inf - inf; a ray parallel to a slab then decides by the sign of
     // (q - o) * 1e28, which the builder's guard band keeps right (kGuardCells)
     g.ix = fminf(fmaxf(g.ix, -1e28f), 1e28f);
@@ -107,60 +98,58 @@ __device__ __forceinline__ GridRay make_grid_ray(const SceneView& sc, V3 o, V3 d
     g.ox = -g.ox * g.ix;
     g.oy = -g.oy * g.iy;
     g.oz = -g.oz * g.iz;
-#endif
+    g.nx = fminf(g.ix, 0.0f);
+    g.ny = fminf(g.iy, 0.0f);
+    g.nz = fminf(g.iz, 0.0f);
     return g;
 }
-__device__ __forceinline__ float slab_t(float q, float o, float i) {
-#if RT_SLAB_FMA
-    return __fmaf_rn(q, i, o);
-#else
-    return (q - o) * i;
-#endif
+// Slab test against a quantised box, three FFMAs per axis and NO per-axis min / max (ncu, round 2: the ALU pipe, which
+// executes FMNMX / SEL / ISETP at half the rate of the FMA pipe, was the busiest pipe of k_extend at 62 %, the FMA pipe
+// idled at 20 %).  With lo the lower plane and ext >= 0 the extent of the box along the axis, both in cells:
+//     t_lo   = fma(lo, i, c)            the ray parameter at the lower plane
+//     t_near = fma(ext, min(i, 0), t_lo)   = t_lo for i >= 0, the upper plane's parameter for i < 0
+//     t_far  = fma(ext, |i|, t_near)       (|.| is a free operand modifier)
+// Conservativeness.  u = 2^-24, Q = 65535 cells, O = |origin| in cells.  The grid transform of the origin costs 2u O,
+// the slope 2u relative, the constant term c = -o i therefore 5u O |i|; t_lo then carries |i| u (3 lo + 6 O), t_near
+// |i| u (6 Q + 7 O) and t_far |i| u (9 Q + 8 O): a plane is displaced by at most u (9 Q + 8 O) cells — 0.066 cell for
+// an origin inside the grid, 0.10 cell at O = 140 000.  The builder rounds every plane outward by kGuardCells = 1/8
+// cell (its own scaling costs another 2u Q = 0.008 cell), so for origins within ~2.1 grid extents rounding can never
+// cull a true hit.  For origins farther out (WIDEN) the far side is widened by 2e-6 relative = 33u |t_far|, which
+// exceeds the sum of both sides' errors, u (15 Q + 15 O), once O > Q.  Slopes are clamped to +-1e28: no inf - inf
+// for rays parallel to a slab.
+// WIDEN = false drops that widening: every bounce ray starts on a surface of the scene, i.e. inside the grid, and so
+// does a camera that stands inside or near the scene box — k_extend is instantiated both ways and the host picks per
+// launch (rt_api.cu: widen_needed).
+constexpr float kWidenFar = 1.000002f;
+constexpr float kSlabMiss = 3.0e38f;
+__device__ __forceinline__ void slab_axis(uint32_t w, float c, float i, float n, float& tNear, float& tFar) {
+    const float tLo = __fmaf_rn(q_lo(w), i, c);
+    const float ext = q_hi(w);
+    tNear = __fmaf_rn(ext, n, tLo);
+    tFar = __fmaf_rn(ext, fabsf(i), tNear);
 }
-// Two slab tests against the quantised child boxes of one node: t = fma(plane, inv, -origin * inv), one FFMA
-// per plane where (plane - origin) * inv needs an FADD and an FMUL (12 fewer instructions per node visit,
-// +2.5 % on config 2).  Conservativeness: with o the origin in cells, the roundings of the grid transform,
-// of the constant term, of the slope and of the fma itself displace a plane by at most
-// 2^-24 * (6|o| + 3 * 65535) cells.  The builder rounds every plane outward by at least kGuardCells = 1/16
-// cell (covers |o| <= 65535, i.e. any origin inside the grid: 0.035 cell) and the far side is widened by
-// 8 ulp relative (covers origins outside it, where |plane - o| grows with |o|), so rounding can never cull
-// a true hit.  Slopes are clamped to +-1e28: no inf - inf for rays parallel to a slab.
-// (RT_SLAB_FMA=0 keeps the subtract-multiply form with a 1e-3 cell guard band.  Selecting near / far planes
-// by direction sign with a byte permute instead of min / max was measured too: 3 more registers cost a
-// resident block per SM and 1.5 %.)
-// WIDEN = false drops the relative widening of the far side: it exists only for origins far outside the grid
-// (|o| beyond ~2.1 grid extents, where the bound above exceeds the guard band); every bounce ray starts on a
-// surface of the scene, i.e. inside the grid, and so does a camera that stands inside or near the scene box —
-// k_extend is instantiated both ways and the host picks per launch (rt_api.cu: widen_needed).
-constexpr float kWidenFar = 1.000001f;
+// One slab test: entry distance, or kSlabMiss.
+template <bool WIDEN = true>
+__device__ __forceinline__ float slab1(uint32_t wx, uint32_t wy, uint32_t wz, const GridRay& g, float bestT) {
+    float nx, fx, ny, fy, nz, fz;
+    slab_axis(wx, g.ox, g.ix, g.nx, nx, fx);
+    slab_axis(wy, g.oy, g.iy, g.ny, ny, fy);
+    slab_axis(wz, g.oz, g.iz, g.nz, nz, fz);
+    const float tn = fmaxf(fmaxf(nx, ny), fmaxf(nz, 0.0f));
+    float tf = fminf(fminf(fx, fy), fminf(fz, bestT));
+    if (WIDEN) tf *= kWidenFar;
+    return tn <= tf ? tn : kSlabMiss;
+}
+// Two slab tests against the child boxes of a binary node.
 template <bool WIDEN = true>
 __device__ __forceinline__ void slab2(const uint32_t (&w)[8], const GridRay& g, float bestT, float& lNear,
                                       float& rNear, bool& hitL, bool& hitR) {
-    const float lx0 = slab_t(q_lo(w[0]), g.ox, g.ix), lx1 = slab_t(q_hi(w[0]), g.ox, g.ix);
-    const float ly0 = slab_t(q_lo(w[1]), g.oy, g.iy), ly1 = slab_t(q_hi(w[1]), g.oy, g.iy);
-    const float lz0 = slab_t(q_lo(w[2]), g.oz, g.iz), lz1 = slab_t(q_hi(w[2]), g.oz, g.iz);
-    const float rx0 = slab_t(q_lo(w[3]), g.ox, g.ix), rx1 = slab_t(q_hi(w[3]), g.ox, g.ix);
-    const float ry0 = slab_t(q_lo(w[4]), g.oy, g.iy), ry1 = slab_t(q_hi(w[4]), g.oy, g.iy);
-    const float rz0 = slab_t(q_lo(w[5]), g.oz, g.iz), rz1 = slab_t(q_hi(w[5]), g.oz, g.iz);
-    lNear = fmaxf(fmaxf(fminf(lx0, lx1), fminf(ly0, ly1)), fmaxf(fminf(lz0, lz1), 0.0f));
-    rNear = fmaxf(fmaxf(fminf(rx0, rx1), fminf(ry0, ry1)), fmaxf(fminf(rz0, rz1), 0.0f));
-    float lFar = fminf(fminf(fmaxf(lx0, lx1), fmaxf(ly0, ly1)), fminf(fmaxf(lz0, lz1), bestT));
-    float rFar = fminf(fminf(fmaxf(rx0, rx1), fmaxf(ry0, ry1)), fminf(fmaxf(rz0, rz1), bestT));
-    if (WIDEN) { lFar *= kWidenFar; rFar *= kWidenFar; }
-    hitL = lNear <= lFar;
-    hitR = rNear <= rFar;
-}
-// One slab test against a quantised box (words lo | hi << 16 per axis): entry distance, or kSlabMiss.
-constexpr float kSlabMiss = 3.0e38f;
-template <bool WIDEN = true>
-__device__ __forceinline__ float slab1(uint32_t wx, uint32_t wy, uint32_t wz, const GridRay& g, float bestT) {
-    const float x0 = slab_t(q_lo(wx), g.ox, g.ix), x1 = slab_t(q_hi(wx), g.ox, g.ix);
-    const float y0 = slab_t(q_lo(wy), g.oy, g.iy), y1 = slab_t(q_hi(wy), g.oy, g.iy);
-    const float z0 = slab_t(q_lo(wz), g.oz, g.iz), z1 = slab_t(q_hi(wz), g.oz, g.iz);
-    const float tn = fmaxf(fmaxf(fminf(x0, x1), fminf(y0, y1)), fmaxf(fminf(z0, z1), 0.0f));
-    float tf = fminf(fminf(fmaxf(x0, x1), fmaxf(y0, y1)), fminf(fmaxf(z0, z1), bestT));
-    if (WIDEN) tf *= kWidenFar;
-    return tn <= tf ? tn : kSlabMiss;
+    const float l = slab1<WIDEN>(w[0], w[1], w[2], g, bestT);
+    const float r = slab1<WIDEN>(w[3], w[4], w[5], g, bestT);
+    hitL = l < kSlabMiss;
+    hitR = r < kSlabMiss;
+    lNear = l;
+    rNear = r;
 }
 // first 48 bytes of a triangle record: a, e0, e1, N
 struct TriGeom {
@@ -226,7 +215,7 @@ __device__ __forceinline__ HitRec closest_hit(const SceneView& sc, V3 o, V3 d, u
     if (sc.num_tris <= 0) return best;
 
     const GridRay g = make_grid_ray(sc, o, d);
-    const float kWiden = 1.000001f;
+    const float kWiden = kWidenFar;
 
     int32_t stack[kStackSize];
     float tstack[kStackSize];

@@ -411,7 +411,7 @@ __global__ void __launch_bounds__(kExtBlock) k_extend(const __grid_constant__ Sc
     uint32_t ray = 0;
     RayRegs r;
     r.o = v3(0, 0, 0); r.d = v3(0, 0, 1); r.bestT = kMissT;
-    r.g.ox = r.g.oy = r.g.oz = r.g.ix = r.g.iy = r.g.iz = 0.0f;
+    r.g.ox = r.g.oy = r.g.oz = r.g.ix = r.g.iy = r.g.iz = r.g.nx = r.g.ny = r.g.nz = 0.0f;
     float bestU = 0, bestV = 0;
     int32_t bestSlot = -1, bestOrig = 0x7fffffff;
     int32_t node = kIdle;
@@ -581,8 +581,12 @@ struct BounceRandoms {
     V3 randDir;
     float d0, d1;
 };
+constexpr int kCoopOwners = 10;  // RT_RNG_PHILOX: pending lanes served per stage-2 pass (3 blocks each: 30 of the 32 lanes work)
+struct CoopSlot {
+    uint32_t pixel, frame, sample, pad;
+};
 // RT_RNG_REF_PCG: the reference's sequential stream, drawn exactly in shader order.
-__device__ __forceinline__ BounceRandoms bounce_randoms(Rng<0>& rng, bool needDir, int nExtra) {
+__device__ __forceinline__ BounceRandoms bounce_randoms(Rng<0>& rng, bool needDir, int nExtra, CoopSlot*) {
     BounceRandoms r;
     r.randDir = v3(0.0f, 0.0f, 0.0f);
     r.d0 = r.d1 = 0.0f;
@@ -591,69 +595,114 @@ __device__ __forceinline__ BounceRandoms bounce_randoms(Rng<0>& rng, bool needDi
     if (nExtra >= 2) r.d1 = rng.next();
     return r;
 }
-// RT_RNG_PHILOX: draw j of a bounce is a pure function of (pixel, frame, sample, bounce, j), so the first
-// twenty draws (five Philox blocks = six rejection tries + the two extra draws after any of them) are
-// generated up front by the whole warp in lock step and the tries are evaluated with selects.  ncu on the
-// sequential version showed 9.5 of 32 lanes active per instruction in k_shade, most of it the divergent
-// rejection loop and the on-demand block generation.  Only the 1.2 % of lanes whose first six tries all
-// fail continue in the sequential loop (from draw 18).  Values and draw indices are identical to the
-// sequential definition, so no bit of the image changes.
+// RT_RNG_PHILOX: draw j of a bounce is a pure function of (pixel, frame, sample, bounce, j): word j & 3 of Philox block
+// j >> 2.  Generating a block costs ~70 instructions, and a lane needs blocks only as far as its rejection loop gets
+// (S:176-183: 3 draws per try, acceptance 52.4 %, then the 1-2 draws after the accepted try): two blocks for 77 % of
+// the lanes, more for the rest.  Round 1 let every lane compute five blocks in lock step (ncu: 9.5 -> 17.6 lanes per
+// instruction, but 75 % of k_shade's instructions were Philox rounds).  Now:
+//   stage 1  every lane computes blocks 0 and 1 of ITS path and evaluates tries 1 and 2 (draws 0..5, extras up to 7);
+//   stage 2  the lanes still without a direction (7 of 32 on average) hand their key to the warp through shared
+//            memory, and lane L computes block 2 + L % 3 FOR pending lane number L / 3: one block-time of the whole
+//            warp produces the three further blocks of up to ten paths; each owner collects its twelve words with
+//            shuffles and evaluates tries 3..6 (draws 6..17, extras up to 19);
+//   tail     the 1.2 % whose six tries all fail continue sequentially from draw 18 as before.
+// Values and draw indices are those of the sequential definition, so no bit of the image changes.
 // The acceptance test of S:180, `length(v) < 1`, is evaluated as `dot(v, v) < 1`: sqrt is correctly rounded and
 // monotonic, the largest float below 1 is 1 - 2^-24 and sqrt(1 - 2^-24) = 1 - 2^-25 - 2^-51 - ... lies below the
 // midpoint of (1 - 2^-24, 1), so it rounds to a value < 1; for x >= 1, sqrt(x) >= 1.  Same decision, no sqrt
 // (tests/test_oracle_cpu.py::test_rejection_test_without_sqrt).
-__device__ __forceinline__ BounceRandoms bounce_randoms(Rng<1>& rng, bool needDir, int nExtra) {
-    constexpr int kBlocks = 5;            // 20 draws: six rejection tries (18) + the two draws after the last
-    constexpr int kTries = 6;             // P(all six fail) = 0.476^6 = 1.2 % of lanes take the sequential tail
+__device__ __forceinline__ BounceRandoms bounce_randoms(Rng<1>& rng, bool needDir, int nExtra, CoopSlot* sWarp) {
+    constexpr uint32_t FULL = 0xffffffffu;
+    const uint32_t lane = threadIdx.x & 31u;
     BounceRandoms r;
     r.randDir = v3(0.0f, 0.0f, 0.0f);
-    if (!__any_sync(0xffffffffu, needDir)) {  // a warp of glass (or finished) paths: draws 0 and 1 only
-        uint32_t w[4];
-        philox4x32_10(0u, rng.bounce, rng.sample, 0x52543230u, rng.pixel, rng.frame, w);
-        r.d0 = u32_to_unit(w[0]);
-        r.d1 = u32_to_unit(w[1]);
-        return r;
+    uint32_t w0[4];
+    philox4x32_10(0u, rng.bounce, rng.sample, 0x52543230u, rng.pixel, rng.frame, w0);
+    r.d0 = u32_to_unit(w0[0]);
+    r.d1 = u32_to_unit(w0[1]);
+    if (!__any_sync(FULL, needDir)) return r;  // a warp of glass (or finished) paths: draws 0 and 1 only
+
+    // ---- stage 1: blocks 0 and 1, tries 1 and 2
+    float f[8];
+#pragma unroll
+    for (int k = 0; k < 4; k++) f[k] = u32_to_unit(w0[k]);
+    {
+        uint32_t w1[4];
+        philox4x32_10(1u, rng.bounce, rng.sample, 0x52543230u, rng.pixel, rng.frame, w1);
+#pragma unroll
+        for (int k = 0; k < 4; k++) f[4 + k] = u32_to_unit(w1[k]);
     }
-    float f[4 * kBlocks];
-    uint32_t lastBlock[4] = {0u, 0u, 0u, 0u};
+    bool found = false;
+    V3 c = v3(0.0f, 0.0f, 0.0f);
+    float d0 = 0.0f, d1 = 0.0f;
 #pragma unroll
-    for (int b = 0; b < kBlocks; b++) {
-        uint32_t w[4];
-        philox4x32_10((uint32_t)b, rng.bounce, rng.sample, 0x52543230u, rng.pixel, rng.frame, w);
-#pragma unroll
-        for (int k = 0; k < 4; k++) f[4 * b + k] = u32_to_unit(w[k]);
-        if (b == kBlocks - 1) {
-#pragma unroll
-            for (int k = 0; k < 4; k++) lastBlock[k] = w[k];
+    for (int t = 0; t < 2; t++) {
+        const V3 cand = v3(f[3 * t] * 2.0f - 1.0f, f[3 * t + 1] * 2.0f - 1.0f, f[3 * t + 2] * 2.0f - 1.0f);
+        const bool acc = !found && dot(cand, cand) < 1.0f;
+        if (acc) {
+            c = cand;
+            d0 = f[3 * t + 3];
+            d1 = f[3 * t + 4];
         }
+        found = found || acc;
     }
-    r.d0 = f[0];
-    r.d1 = f[1];
-    if (needDir) {
-        // all tries evaluated in lock step; the FIRST accepted one wins, exactly as the sequential loop
-        bool found = false;
-        V3 c = v3(0.0f, 0.0f, 0.0f);
-        float d0 = 0.0f, d1 = 0.0f;
+    // ---- stage 2: the pending lanes' blocks 2, 3, 4 computed by the whole warp, kCoopOwners paths per pass
+    bool pending = needDir && !found;
+    uint32_t last[4] = {0u, 0u, 0u, 0u};  // block 4 of a lane that goes on to the sequential tail
+    bool exhausted = false;               // all six tries failed
+    for (uint32_t U = __ballot_sync(FULL, pending); U != 0u; U = __ballot_sync(FULL, pending)) {
+        const uint32_t rank = (uint32_t)__popc(U & ((1u << lane) - 1u));
+        const bool owner = pending && rank < (uint32_t)kCoopOwners;
+        const uint32_t served = min((uint32_t)__popc(U), (uint32_t)kCoopOwners);
+        if (owner) sWarp[rank] = CoopSlot{rng.pixel, rng.frame, rng.sample, 0u};
+        __syncwarp();
+        uint32_t w[4] = {0u, 0u, 0u, 0u};
+        const uint32_t job = lane / 3u;
+        if (job < served) {
+            const CoopSlot key = sWarp[job];
+            philox4x32_10(2u + (lane - 3u * job), rng.bounce, key.sample, 0x52543230u, key.pixel, key.frame, w);
+        }
+        __syncwarp();  // the slots are rewritten by the next pass
+        // draws 6..19 of an owner: 6, 7 from its own block 1, 8..19 from lanes 3 rank .. 3 rank + 2
+        float g[14];
+        g[0] = f[6];
+        g[1] = f[7];
+        const uint32_t src = owner ? 3u * rank : lane;
 #pragma unroll
-        for (int t = 0; t < kTries; t++) {
-            const V3 cand = v3(f[3 * t] * 2.0f - 1.0f, f[3 * t + 1] * 2.0f - 1.0f, f[3 * t + 2] * 2.0f - 1.0f);
-            const bool acc = !found && dot(cand, cand) < 1.0f;
-            if (acc) {
-                c = cand;
-                d0 = f[3 * t + 3];
-                d1 = f[3 * t + 4];
+        for (int b = 0; b < 3; b++) {
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const uint32_t v = __shfl_sync(FULL, w[k], (src + b) & 31u);
+                g[2 + 4 * b + k] = u32_to_unit(v);
+                if (b == 2) last[k] = owner ? v : last[k];
             }
-            found = found || acc;
         }
+        if (owner) {
+#pragma unroll
+            for (int t = 0; t < 4; t++) {  // tries 3..6: draws 6 + 3 t .. 8 + 3 t, extras 9 + 3 t and 10 + 3 t
+                const V3 cand = v3(g[3 * t] * 2.0f - 1.0f, g[3 * t + 1] * 2.0f - 1.0f, g[3 * t + 2] * 2.0f - 1.0f);
+                const bool acc = !found && dot(cand, cand) < 1.0f;
+                if (acc) {
+                    c = cand;
+                    d0 = g[3 * t + 3];
+                    d1 = g[3 * t + 4];
+                }
+                found = found || acc;
+            }
+            exhausted = !found;
+            pending = false;
+        }
+    }
+    if (needDir) {
         if (found) {
             r.randDir = normalize(c);
             r.d0 = d0;
             r.d1 = d1;
-        } else {
-            // tries 7..100 of S:176-183, sequentially, from draw 18 (the last block is already in hand)
-            rng.j = 3u * kTries;
-            rng.cache[0] = lastBlock[0]; rng.cache[1] = lastBlock[1]; rng.cache[2] = lastBlock[2]; rng.cache[3] = lastBlock[3];
-            for (int i = kTries; i < 100; i++) {
+        } else if (exhausted) {
+            // tries 7..100 of S:176-183, sequentially, from draw 18 (block 4 is already in hand)
+            rng.j = 18u;
+            rng.cache[0] = last[0]; rng.cache[1] = last[1]; rng.cache[2] = last[2]; rng.cache[3] = last[3];
+            for (int i = 6; i < 100; i++) {
                 const float x = rng.next() * 2.0f - 1.0f;
                 const float y = rng.next() * 2.0f - 1.0f;
                 const float z = rng.next() * 2.0f - 1.0f;
@@ -687,6 +736,7 @@ __global__ void __launch_bounds__(kBlock, 4) k_shade(const __grid_constant__ Sce
                                                   float4* __restrict__ contrib, uint32_t* __restrict__ pix_rng,
                                                   const uint32_t* __restrict__ countIn,
                                                   uint32_t* __restrict__ countOut, int bounce) {
+    __shared__ CoopSlot sCoop[kBlock / 32][kCoopOwners];  // stage 2 of bounce_randoms: keys handed to the warp
     const uint32_t n = *countIn;
     const uint32_t lane = threadIdx.x & 31u;
     constexpr uint32_t FULL = 0xffffffffu;
@@ -734,7 +784,8 @@ __global__ void __launch_bounds__(kBlock, 4) k_shade(const __grid_constant__ Sce
         BounceRandoms rnd;
         rnd.randDir = v3(0.0f, 0.0f, 0.0f);
         rnd.d0 = rnd.d1 = 0.0f;
-        if (MODE == 0 || __any_sync(FULL, needDir || nExtra > 0)) rnd = bounce_randoms(rng, needDir, nExtra);
+        if (MODE == 0 || __any_sync(FULL, needDir || nExtra > 0))
+            rnd = bounce_randoms(rng, needDir, nExtra, sCoop[threadIdx.x >> 5]);
         if (valid) {
             bool terminated = false;
             V3 radiance = v3(0.0f, 0.0f, 0.0f);

@@ -688,17 +688,23 @@ def test_kernel_variants_change_no_bit(monkeypatch, env, rng_mode):
 
 def test_camera_far_outside_the_scene_uses_the_widened_slabs(classic):
     """rt_scene.cuh drops the relative widening of the slab test's far side when the camera stands within ~2 grid
-    extents of the scene; beyond that the widened variant must run.  Both must give the oracle's first-hit map."""
+    extents of the scene; beyond that the widened variant must run.  Either way the first-hit map must equal the
+    EXHAUSTIVE minimum over all triangles (the oracle without its BVH: at t = 4000 the reference builder's 1e-4 box
+    padding is below one ulp of t, so the oracle's own tree is not the judge there); frames are compared where the
+    oracle's tree is reliable."""
     scene, orc = classic
     for z in (15.5, 60.0, 4000.0):
         cam = rt.make_camera(64, 64, (0.0, 0.0, z), hfov=0.5 * 10.0 / z)
         u = rt.screenshot_uniforms(scene, cam, spp=2, max_bounce=4, env_light=False)
         be = backend(scene)
-        be.render_frame(u)
-        assert_image_equal(be.read_frame(), orc.render_frame(u, rng_mode=rt.RNG_PHILOX), f"camera at z={z}")
-        tri, dst = be.first_hit(u, rt.FIRST_HIT_CENTRE)
-        otri, odst = orc.first_hit(u, rt.FIRST_HIT_CENTRE)
-        assert np.array_equal(tri, otri) and np.array_equal(bits(dst), bits(odst))
+        for mode in (rt.FIRST_HIT_CENTRE, rt.FIRST_HIT_SAMPLE0):
+            tri, dst = be.first_hit(u, mode)
+            otri, odst = orc.first_hit(u, mode, rng_mode=rt.RNG_PHILOX, use_bvh=False)
+            assert np.array_equal(tri, otri) and np.array_equal(bits(dst), bits(odst)), f"camera at z={z}"
+        assert (tri >= 0).mean() > 0.5
+        if z < 100.0:
+            be.render_frame(u)
+            assert_image_equal(be.read_frame(), orc.render_frame(u, rng_mode=rt.RNG_PHILOX), f"camera at z={z}")
         be.close()
 
 

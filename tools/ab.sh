@@ -9,7 +9,8 @@ try:
     d = json.loads(sys.argv[2])
     r = d["roofline"]
     print(f"[{sys.argv[1] or 'default'}] {d['value']:.0f} Mrays/s  {d['ms_per_step']:.1f} ms/step  extend {r['t_measured_ms']:.2f} ms/launch  "
-          f"share {r['extend_share_of_step']:.3f}  crc {d['checksum']} gate {d['parity_gate'].get('screenshot')}")
+          f"share {r['extend_share_of_step']:.3f}  visits {r['node_visits_per_segment']:.2f} tris {r['tri_tests_per_segment']:.2f} build {d['bvh']['build_ms']:.2f} ms "
+          f"crc {d['checksum']} gate {d['parity_gate'].get('screenshot')}")
 except Exception as e:
     print(f"[{sys.argv[1]}] FAILED: {sys.argv[2][-400:]}")
 PY
