@@ -101,7 +101,7 @@ def workload_config(name, frames_total, n_gpus, split):
         "frames_total": int(frames_total),
         "split": "frame-slice (frame f on rank f % N) + ncclReduce of the 8-bit frame sums to rank 0" if split == "frames"
                  else "image-tile (bands of 8 rows dealt round-robin) + gather of each rank's rows to rank 0",
-        "cache": "the path state of one wavefront batch (up to 128 Mi paths x 128 B = 16 GiB) is far larger than the "
+        "cache": "the path state of one wavefront batch (up to 512 Mi paths x 128 B = 64 GiB) is far larger than the "
                  "126 MB L2 and is rewritten every bounce: inputs larger than L2, no explicit flush",
     }
 

@@ -150,7 +150,7 @@ typedef struct rt_config {
                                of the same kernels; never used for timed runs)                   */
     int32_t kernel_timing;  /* 1 = bracket every kernel with CUDA events on the ctx stream and report
                                per-class device time through rt_get_counters (small overhead)    */
-    uint64_t max_paths_in_flight; /* path slots kept resident (128 B each); 0 = auto: 128 Mi slots,
+    uint64_t max_paths_in_flight; /* path slots kept resident (128 B each); 0 = auto: 512 Mi slots,
                                      capped at 40 % of the free device memory                       */
 } rt_config;
 

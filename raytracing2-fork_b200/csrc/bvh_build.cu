@@ -353,7 +353,9 @@ __global__ void __launch_bounds__(256) k_refit(const rt_triangle* __restrict__ t
 }
 
 // --------------------------------------------------------------------------------------------- PLOC
-constexpr int kPlocRadiusDefault = 10;  // search window of the clustering (RT_PLOC_RADIUS overrides, 1..64)
+// search window of the clustering (RT_PLOC_RADIUS overrides, 1..64).  Measured on config 2 (profiles/r2_knobs_ab.txt):
+// radius 6 -> 7.13 wide-node visits per segment, 10 -> 7.24, 16 / 25 / 40 -> slightly MORE visits and a slower build.
+constexpr int kPlocRadiusDefault = 6;
 
 // leaf boxes in Morton order (entity n-1+slot), cluster list = all leaves
 __global__ void __launch_bounds__(256) k_ploc_init(const rt_triangle* __restrict__ tris,

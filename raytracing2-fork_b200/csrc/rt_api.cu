@@ -109,7 +109,7 @@ struct rt_ctx {
     rt_config cfg{};
     int sm_count = 148;
     int extend_blocks_per_sm = 4;
-    int leaf_vote = 12, refill = 8, node_steps = 4;
+    int leaf_vote = 14, refill = 8, node_steps = 4;
     int node_steps_wide = 2, extend_blocks_per_sm_wide = 8;
     int use_ploc = 1, dfs_layout = 1, speculative = 1, shade_blocks_per_sm = 64;
     int top_smem = 0;              // RT_EXT_TOP=1: k_extend keeps the top four levels of the wide tree in shared memory
@@ -129,7 +129,7 @@ struct rt_ctx {
     int l2_max_persist = -1, l2_max_window = 0;  // device limits, -1 = not queried yet
     const void* l2_win_base = nullptr;           // the access-policy window currently set on the stream
     size_t l2_win_bytes = 0;
-    uint64_t default_budget = (uint64_t)128 << 20;  // path slots in flight (128 B each = 16 GiB; capped by free memory)
+    uint64_t default_budget = (uint64_t)512 << 20;  // path slots in flight (128 B each = 64 GiB; capped at 40 % of the free memory)
     cudaStream_t own_stream = nullptr;
     cudaStream_t stream = nullptr;
     std::string err;
@@ -593,8 +593,9 @@ int rt_create(rt_ctx** out, const rt_config* cfg) {
     ctx->extend_blocks_per_sm_top = wf_extend_blocks_per_sm(false, true, true);
     {
         // Path slots: fewer, larger wavefronts amortise the drain of the persistent kernels (config 2: 8 lanes
-        // per pixel 1203 ms/step, 64 lanes 1057 ms).  HBM is there to be used: default 128 Mi slots = 16 GiB,
-        // never more than 40 % of what is free.
+        // per pixel 1203 ms/step, 64 lanes 1057 ms; round 2: 128 Mi slots 744.8 ms, 512 Mi — the whole 4-frame
+        // screenshot in one wavefront, a 4K frame in one — 735.5 ms).  HBM is there to be used: default 512 Mi slots
+        // = 64 GiB, never more than 40 % of what is free, and only what a job needs is ever allocated.
         size_t freeB = 0, totalB = 0;
         if (cudaMemGetInfo(&freeB, &totalB) == cudaSuccess && freeB > 0)
             ctx->default_budget = std::min<uint64_t>(ctx->default_budget, (uint64_t)(freeB * 0.4) / 128u);
