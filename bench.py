@@ -311,13 +311,14 @@ def run_reference(args, rt):
 
 
 # ------------------------------------------------------------------------------------------------ roofline
-def load_traffic(name, width):
-    """dram__bytes per segment of k_extend from the committed ncu --set full capture of the CURRENT kernel
-    (profiles/extend_traffic.json: one entry per workload with the kernel's git hash and the capture's file)."""
+def load_traffic(name):
+    """dram__bytes per segment of k_extend, measured with ncu over every k_extend launch of one screenshot of this
+    workload (tools/extend_traffic.sh -> profiles/extend_traffic.json: per workload the bytes, the kernel's git hash,
+    the date and the raw CSV)."""
     try:
         t = json.load(open(os.path.join(REPO, "profiles", "extend_traffic.json")))
-        e = t.get(name) or t.get("config2" if name == "4k" else name)
-        return e
+        e = t.get(name)
+        return e if isinstance(e, dict) else None
     except Exception:
         return None
 
@@ -346,11 +347,15 @@ def extend_roofline(c, ci, ceil, name, bvh_bytes, ms_total, clocks, width_of_tre
     if not fp32_peak or fp32_peak <= 0:
         sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
         fp32_peak, fp32_src = 148 * 128 * sm_mhz * 1e6 * 1e-12, "estimate 148 SM x 128 lanes x SM clock"
+    tr = load_traffic(name)
+    dram_b = tr.get("dram_bytes_per_segment") if tr else None
     t = {}
-    # HBM: the path records always stream through HBM; the BVH bytes only when the BVH cannot live in L2
+    # HBM: the path records always stream through HBM; the BVH bytes only when the BVH cannot live in L2 (then ALL of
+    # them are charged to HBM at the copy peak, although the top of the tree is served by L1 / L2: an upper bound on
+    # the HBM time, i.e. the most demanding of the ceilings that can be written down without a cache model)
     t["hbm"] = (path_b + (0.0 if l2_resident else bvh_b)) * seg_per_launch / (hbm_peak * 1e9)
-    if gather_peak and gather_peak > 0:
-        t["l2_gather" if l2_resident else "hbm_gather"] = bvh_b * seg_per_launch / (gather_peak * 1e9)
+    if l2_resident and gather_peak and gather_peak > 0:
+        t["l2_gather"] = bvh_b * seg_per_launch / (gather_peak * 1e9)
     t["fp32"] = flops * seg_per_launch / (fp32_peak * 1e12)
     bound = max(t, key=lambda k: t[k])
     t_roof = t[bound]
@@ -360,14 +365,20 @@ def extend_roofline(c, ci, ceil, name, bvh_bytes, ms_total, clocks, width_of_tre
         achieved, peak, unit = (path_b + (0.0 if l2_resident else bvh_b)) * seg_per_launch / t_meas * 1e-9, hbm_peak, "GB/s"
     else:
         achieved, peak, unit = bvh_b * seg_per_launch / t_meas * 1e-9, gather_peak, "GB/s"
-    tr = load_traffic(name, width_of_tree)
-    traffic = None
-    if tr and tr.get("dram_bytes_per_segment") is not None:
-        traffic = tr["dram_bytes_per_segment"] * seg_per_launch
+    traffic = dram_b * seg_per_launch if dram_b is not None else None
+    # for the record, not a ceiling of algorithmic bytes: the DRAM bytes ncu counted, delivered in the time measured
+    # here, against what HBM delivers (a) streaming and (b) as random 64-byte gathers out of a 1 GB table
+    dram = None
+    if dram_b is not None and t_meas > 0:
+        gbs = dram_b * seg_per_launch / t_meas * 1e-9
+        hg = g.get("1GB_64B_independent")
+        dram = {"bytes_per_segment": dram_b, "gbs": gbs, "frac_of_hbm_copy_peak": gbs / hbm_peak,
+                "frac_of_hbm_random_gather_peak": (gbs / hg) if hg else None, "hbm_random_gather_gbs": hg,
+                "algorithmic_bytes_served_on_chip": 1.0 - min(1.0, dram_b / (bvh_b + path_b))}
     return {
         "kernel": "k_extend", "bound": bound, "achieved": achieved, "peak": peak, "unit": unit,
         "frac": t_roof / t_meas if t_meas > 0 else None, "traffic": traffic,
-        "traffic_source": tr,
+        "traffic_source": tr, "dram_measured": dram,
         "t_measured_ms": t_meas * 1e3, "t_roof_ms": {k: v * 1e3 for k, v in t.items()},
         "frac_by_ceiling": {k: (v / t_meas if t_meas > 0 else None) for k, v in t.items()},
         "peaks": {"hbm_gbs": hbm_peak, "hbm_source": hbm_src, "gather_gbs": gather_peak,
@@ -382,6 +393,22 @@ def extend_roofline(c, ci, ceil, name, bvh_bytes, ms_total, clocks, width_of_tre
                 "throughput); counts from an instrumented replay of identical rays (counter-based RNG); duration = average "
                 "k_extend launch of the timed region (CUDA events on the launching stream); frac = largest t_roof / t_measured",
     }
+
+
+def shade_roofline(c, ms_total):
+    """Everything outside k_extend streams path records through HBM (k_raygen, k_shade, k_accumulate, k_resolve; DESIGN.md
+    §5): algorithmic bytes = per segment 64 read (48 B state + 16 B hit), per surviving segment 48 written, per path
+    48 written by raygen, 16 written as its contribution and 16 read back by k_accumulate — against the measured
+    HBM copy peak, over the device time the library's events give that kernel class."""
+    S, P = float(c["segments"]), float(c["paths"])
+    if S <= 0 or c["shade_ms"] <= 0:
+        return None
+    total = 64.0 * S + 48.0 * (S - P) + (48.0 + 16.0 + 16.0) * P
+    hbm_peak, _ = measured_peaks()
+    gbs = total / (c["shade_ms"] * 1e-3) * 1e-9
+    return {"kernels": "k_raygen + k_shade + k_accumulate + k_resolve", "bound": "hbm", "achieved": gbs, "peak": hbm_peak,
+            "unit": "GB/s", "frac": gbs / hbm_peak, "bytes_per_segment": total / S,
+            "share_of_step": c["shade_ms"] / ms_total if ms_total else None}
 
 
 # ------------------------------------------------------------------------------------------------ GPU arm
@@ -553,7 +580,7 @@ def side_block(R, rt, name, frames, steps, warmup, ceil):
     return {"workload": wl["text"], "frames_timed": frames, "frames_of_config": wl["frames"],
             "value": m["value"], "unit": "Mrays/s", "ms_per_step": m["ms_per_step"], "steps": steps, "warmup": warmup,
             "seconds_per_full_screenshot": m["ms_per_step"] * 1e-3 * wl["frames"] / frames,
-            "roofline": roof, "parity_gate": gate,
+            "roofline": roof, "shade_roofline": shade_roofline(c, m["ms_total"]), "parity_gate": gate,
             "bvh": {"build_ms": c["build_ms"], "nodes": c["bvh_nodes"], "bytes": c["bvh_bytes"], "depth": c["bvh_depth"],
                     "width": c["bvh_width"], "stack_need": c["bvh_stack_need"], "build_rounds": c["bvh_build_rounds"]}}
 
@@ -630,7 +657,8 @@ def run_gpu(args, rt):
             "seconds_per_screenshot": m["ms_per_step"] * 1e-3, "step_ms": [round(x, 2) for x in m["step_ms"]],
             "segments_per_step": m["segments"] / args.steps,
             "e2e": e2e, "gpu_launches": int(m["launches"]),
-            "roofline": roof, "ceilings": ceil, "cpu_baseline": cpu, "clocks": m["clocks"], "parity_gate": gate,
+            "roofline": roof, "shade_roofline": shade_roofline(c, m["ms_total"]) if world == 1 else None,
+            "ceilings": ceil, "cpu_baseline": cpu, "clocks": m["clocks"], "parity_gate": gate,
             "bvh": {"build_ms": c["build_ms"], "nodes": c["bvh_nodes"], "bytes": c["bvh_bytes"], "depth": c["bvh_depth"],
                     "width": c["bvh_width"], "stack_need": c["bvh_stack_need"], "build_rounds": c["bvh_build_rounds"]},
             "checksum": gate.get("screenshot_crc") if gate else None,

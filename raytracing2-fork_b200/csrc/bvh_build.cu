@@ -96,6 +96,34 @@ __global__ void __launch_bounds__(256) k_tri_bounds(const rt_triangle* __restric
     }
 }
 
+// Upload-time validation (rt_scene_set_triangles): a vertex coordinate that is NaN, inf or beyond 1e18 in magnitude.
+// Within that range every box extent and every surface area the builder forms stays finite, so the build itself can
+// run without ever looking at a status word on the host.  One pass at HBM speed, read back with the sync the upload
+// needs anyway.
+__global__ void __launch_bounds__(256) k_validate_tris(const rt_triangle* __restrict__ tris, int n,
+                                                       uint32_t* __restrict__ flag) {
+    bool bad = false;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const float4 a = *reinterpret_cast<const float4*>(tris[i].a);
+        const float4 b = *reinterpret_cast<const float4*>(tris[i].b);
+        const float4 c = *reinterpret_cast<const float4*>(tris[i].c);
+        const float m = fmaxf(fmaxf(fmaxf(fabsf(a.x), fabsf(a.y)), fmaxf(fabsf(a.z), fabsf(b.x))),
+                              fmaxf(fmaxf(fabsf(b.y), fabsf(b.z)), fmaxf(fabsf(c.x), fmaxf(fabsf(c.y), fabsf(c.z)))));
+        // fmaxf drops NaN operands, so test them separately: x != x
+        const bool nan = a.x != a.x || a.y != a.y || a.z != a.z || b.x != b.x || b.y != b.y || b.z != b.z ||
+                         c.x != c.x || c.y != c.y || c.z != c.z;
+        bad |= nan || !(m <= 1.0e18f);
+    }
+    if (__any_sync(0xffffffffu, bad) && (threadIdx.x & 31) == 0) atomicOr(flag, 1u);
+}
+cudaError_t validate_triangles(const rt_triangle* tris, int n, uint32_t* flag, int sm_count, cudaStream_t st) {
+    cudaError_t e = cudaMemsetAsync(flag, 0, sizeof(uint32_t), st);
+    if (e != cudaSuccess || n <= 0) return e;
+    const int blocks = std::min((n + 255) / 256, sm_count * 8);
+    k_validate_tris<<<blocks, 256, 0, st>>>(tris, n, flag);
+    return cudaGetLastError();
+}
+
 __device__ __forceinline__ uint64_t spread21(uint32_t v) {  // 21 bits → every third bit
     uint64_t x = v & 0x1fffffu;
     x = (x | x << 32) & 0x1f00000000ffffull;

@@ -140,6 +140,7 @@ struct rt_ctx {
     int32_t n_mats = 0;
     bool built = false;
     int32_t max_mat_index = -1;
+    bool tris_out_of_range = false;  // the uploaded triangles hold a NaN / inf / > 1e18 coordinate (checked at upload)
     uint32_t bvh_depth = 0;
 
     DevBuf d_tris, d_mats, d_tex[RT_MAX_TEXTURES];
@@ -678,9 +679,15 @@ int rt_scene_set_triangles(rt_ctx* ctx, const rt_triangle* tris, int64_t count) 
     ctx->max_mat_index = -1;
     CK(ctx->d_tris.reserve(std::max<size_t>((size_t)count, 1) * sizeof(rt_triangle)));
     if (count) CK(cudaMemcpyAsync(ctx->d_tris.p, tris, (size_t)count * sizeof(rt_triangle), cudaMemcpyHostToDevice, ctx->stream));
+    // coordinate range check on the device copy (one pass at HBM speed), read back with the sync the upload needs anyway
+    uint32_t outOfRange = 0;
+    CK(ctx->d_depth.reserve(kBuildStatusWords * sizeof(uint32_t)));
+    CK(validate_triangles(ctx->d_tris.as<rt_triangle>(), (int)count, ctx->d_depth.as<uint32_t>(), ctx->sm_count, ctx->stream));
+    CK(cudaMemcpyAsync(&outOfRange, ctx->d_depth.p, sizeof outOfRange, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));  // glBufferData semantics: the caller may free at once
     ctx->n_tris = count;
     ctx->max_mat_index = maxMat;
+    ctx->tris_out_of_range = outOfRange != 0;
     return RT_OK;
 }
 
@@ -721,6 +728,8 @@ int rt_scene_build(rt_ctx* ctx) {
     const int n = (int)ctx->n_tris;
     ctx->built = false;
     ctx->wide_ok = false;
+    if (ctx->tris_out_of_range)  // not sticky: upload a finite scene and build again
+        return fail(ctx, RT_ERR_INVALID, "rt_scene_build: a triangle has a non-finite vertex coordinate (NaN, inf or |x| > 1e18)");
     if (n == 0) {
         ctx->built = true;
         ctx->bvh_depth = 0;

@@ -46,6 +46,8 @@ constexpr int kBuildPlocRounds = 3;  // rounds the clustering took (diagnostic)
 constexpr int kBuildStatusWords = 4;
 cudaError_t build_lbvh(const BuildArgs& a, cudaStream_t st, uint64_t* launches);
 size_t build_scratch_words(int n);
+// sets *flag (device word) to 1 if a vertex coordinate is NaN, inf or larger than 1e18 in magnitude
+cudaError_t validate_triangles(const rt_triangle* tris, int n, uint32_t* flag, int sm_count, cudaStream_t st);
 
 // ---------------------------------------------------------------- wavefront.cu
 // Path state of the wavefront, structure of arrays, 16-byte records, ping-ponged between bounces

@@ -63,18 +63,33 @@ __device__ __forceinline__ void ldg256u(const void* p, uint32_t (&v)[8]) {
                  : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
                  : "l"(p));
 }
-// exact uint16 -> float.  RT_DEQ_I2F: one I2F.U16 per plane (reads the half register directly, XU
-// pipe); otherwise splice into the mantissa of 2^23 and subtract 2^23 (LOP3 + FADD, ALU/FMA pipes).
-#ifndef RT_DEQ_I2F
-#define RT_DEQ_I2F 1
+// exact uint16 -> float, two ways with identical results:
+//   I2F.U16   one instruction that reads the half register directly, but on the XU pipe: 16 lanes / clk / SM
+//             (tools/microbench.cu: 4.5 T/s against 17.8 T/s FFMA instructions);
+//   magic     splice the 16 bits into the mantissa of 2^23 (one PRMT / LOP3 on the ALU pipe, 64 lanes / clk) and
+//             subtract 2^23 (one FADD on the FMA pipe, 128 lanes / clk, 75 % idle in k_extend).
+// A 4-wide visit converts 24 planes; all on XU that is 192 pipe cycles per warp against ~131 issue slots — ncu round 2:
+// XU 54 % busy, the busiest pipe relative to its rate.  RT_DEQ_MODE picks per half-word: bit 0 = upper half by magic,
+// bit 1 = lower half by magic.  Measured on config 2 (profiles/r2_deq_ab.txt): mode 0 (all I2F) 5880 Mrays/s, mode 1
+// 5746, mode 2 5787, mode 3 5580 — the kernel is bound by issue slots, not by the XU pipe: the second instruction per
+// plane costs more than the slow pipe.  Default 0.
+#ifndef RT_DEQ_MODE
+#define RT_DEQ_MODE 0
 #endif
-#if RT_DEQ_I2F
-__device__ __forceinline__ float q_lo(uint32_t w) { return (float)(uint16_t)(w & 0xffffu); }
-__device__ __forceinline__ float q_hi(uint32_t w) { return (float)(uint16_t)(w >> 16); }
+__device__ __forceinline__ float q_lo(uint32_t w) {
+#if RT_DEQ_MODE & 2
+    return __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7610)) - 8388608.0f;
 #else
-__device__ __forceinline__ float q_lo(uint32_t w) { return __uint_as_float(0x4B000000u | (w & 0xffffu)) - 8388608.0f; }
-__device__ __forceinline__ float q_hi(uint32_t w) { return __uint_as_float(0x4B000000u | (w >> 16)) - 8388608.0f; }
+    return (float)(uint16_t)(w & 0xffffu);
 #endif
+}
+__device__ __forceinline__ float q_hi(uint32_t w) {
+#if RT_DEQ_MODE & 1
+    return __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7632)) - 8388608.0f;
+#else
+    return (float)(uint16_t)(w >> 16);
+#endif
+}
 
 // The ray in grid coordinates: per-axis scaling of origin and direction leaves t unchanged.
 struct GridRay {
