@@ -267,6 +267,17 @@ __global__ void __launch_bounds__(kBlock) k_raygen(const __grid_constant__ Frame
 // The closest-hit rule (min dst, then lowest original index) makes the result independent of the
 // order in which lanes, nodes and triangles are visited, so the restructuring changes no bit.
 constexpr int kExtBlock = 128;
+// experiment switches (tools/build_variant.sh): software prefetch of the streaming path records into L2
+#ifndef RT_EXT_PREFETCH
+#define RT_EXT_PREFETCH 0
+#endif
+#ifndef RT_SHADE_PREFETCH
+#define RT_SHADE_PREFETCH 0
+#endif
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+#ifndef RT_EXT_MIN_BLOCKS
+#define RT_EXT_MIN_BLOCKS 9   // 56 registers: nine resident blocks per SM (ten at 48 registers measured 0.8 % slower, eight slower too)
+#endif
 constexpr int32_t kPop = (int32_t)0x80000000;       // lane state: take the next subtree from the stack
 constexpr int32_t kIdle = (int32_t)0x80000001;      // lane state: no ray
 struct ExtendTune {
@@ -386,7 +397,7 @@ __device__ __forceinline__ bool is_leaf_code(int32_t x) { return x < 0 && (uint3
 // out of nodes).  Node steps then run with more lanes, leaf steps test up to two leaves per lane; the price
 // is a stale bestT while a leaf is parked (a few more node visits).  Selected at run time (RT_EXT_SPEC).
 template <bool COUNT, bool SPEC, bool WIDE, bool WIDEN, bool TOP>
-__global__ void __launch_bounds__(kExtBlock) k_extend(const __grid_constant__ SceneView sc, PathArrays cur,
+__global__ void __launch_bounds__(kExtBlock, RT_EXT_MIN_BLOCKS) k_extend(const __grid_constant__ SceneView sc, PathArrays cur,
                                                       float4* __restrict__ hit, const uint32_t* __restrict__ count,
                                                       uint32_t* __restrict__ cursor, ExtendTune tune,
                                                       unsigned long long* __restrict__ stats) {
@@ -425,24 +436,28 @@ __global__ void __launch_bounds__(kExtBlock) k_extend(const __grid_constant__ Sc
     }
 
     // exact Möller–Trumbore against every triangle of one leaf; min (dst, original index) wins
-    auto test_leaf = [&](int32_t code) {
-        const int32_t packed = ~code;
-        const int32_t first = packed & kLeafFirstMask;
-        const int32_t cnt = (packed >> kLeafCountShift) + 1;
-        for (int32_t s = first; s < first + cnt; s++) {
-            const TriGeom tg = load_tri(sc, s);
-            if (COUNT) tests++;
-            float dst, u, v;
-            if (ray_triangle(r.o, r.d, tg.a, tg.e0, tg.e1, tg.N, dst, u, v)) {
-                if (dst <= r.bestT && dst < kMissT) {
-                    const int32_t orig = __ldg(&sc.tri_orig[s]);
-                    if (dst < r.bestT || orig < bestOrig) {
-                        r.bestT = dst; bestU = u; bestV = v; bestSlot = s; bestOrig = orig;
-                    }
+    auto test_tri = [&](int32_t s) {
+        const TriGeom tg = load_tri(sc, s);
+        if (COUNT) tests++;
+        float dst, u, v;
+        if (ray_triangle(r.o, r.d, tg.a, tg.e0, tg.e1, tg.N, dst, u, v)) {
+            if (dst <= r.bestT && dst < kMissT) {
+                const int32_t orig = __ldg(&sc.tri_orig[s]);
+                if (dst < r.bestT || orig < bestOrig) {
+                    r.bestT = dst; bestU = u; bestV = v; bestSlot = s; bestOrig = orig;
                 }
             }
         }
     };
+    auto test_leaf = [&](int32_t code) {
+        const int32_t packed = ~code;
+        const int32_t first = packed & kLeafFirstMask;
+        const int32_t cnt = (packed >> kLeafCountShift) + 1;
+        for (int32_t s = first; s < first + cnt; s++) test_tri(s);
+    };
+    // (Round 2 measured the two leaves of a lane as ONE merged triangle sequence — the warp iterates max(cntA + cntB)
+    // instead of max(cntA) + max(cntB): 5781 vs 5853 Mrays/s, the per-iteration select costs more than the shorter loop
+    // saves; profiles/r2_leafmerge_shadeocc_ab.txt.)
     // one stack entry; entries that can no longer hold a hit are dropped
     auto pop_one = [&]() {
         --sp;
@@ -511,6 +526,10 @@ __global__ void __launch_bounds__(kExtBlock) k_extend(const __grid_constant__ Sc
             base = __shfl_sync(FULL, base, leader);
             if (node == kIdle) {
                 const uint32_t i = base + __popc(idle & ltMask);
+                if (RT_EXT_PREFETCH) {  // the record a lane of this grid will claim about one refill generation from now
+                    const uint32_t ahead = i + gridDim.x * kExtBlock;
+                    if (ahead < n) { prefetch_l2(&cur.od0[ahead]); prefetch_l2(&cur.od1[ahead]); }
+                }
                 if (i < n) {
                     const float4 a = cur.od0[i];
                     const float4 b = cur.od1[i];
@@ -540,8 +559,8 @@ __global__ void __launch_bounds__(kExtBlock) k_extend(const __grid_constant__ Sc
             if (SPEC) {
                 if (post != kNoLeaf) {
                     test_leaf(post);
-                    post = kNoLeaf;
                     if (is_leaf_code(node)) test_leaf(node);
+                    post = kNoLeaf;
                     if (parked) node = kPop;
                 }
             } else if (parked) {
@@ -729,8 +748,11 @@ __device__ __forceinline__ BounceRandoms bounce_randoms(Rng<1>& rng, bool needDi
 // texture fetch diverges.  What is kept from that work: the random numbers of a bounce are drawn by the converged
 // warp, and a warp whose paths all end (miss, light, unknown material) draws none.
 // One bounce of S:481-560 for every live path.  `bounce` is the 0-based index of this segment.
+#ifndef RT_SHADE_MIN_BLOCKS
+#define RT_SHADE_MIN_BLOCKS 4   // 64 registers; 5 blocks (48 registers, 358 B of spills) -15 %, 6 blocks -16 % (profiles/r2_leafmerge_shadeocc_ab.txt)
+#endif
 template <int MODE>
-__global__ void __launch_bounds__(kBlock, 4) k_shade(const __grid_constant__ SceneView sc,
+__global__ void __launch_bounds__(kBlock, RT_SHADE_MIN_BLOCKS) k_shade(const __grid_constant__ SceneView sc,
                                                   const __grid_constant__ FrameParams fp, PathArrays cur,
                                                   PathArrays next, const float4* __restrict__ hit,
                                                   float4* __restrict__ contrib, uint32_t* __restrict__ pix_rng,
@@ -743,6 +765,10 @@ __global__ void __launch_bounds__(kBlock, 4) k_shade(const __grid_constant__ Sce
     for (uint32_t base = blockIdx.x * kBlock; base < n; base += gridDim.x * kBlock) {
         const uint32_t i = base + threadIdx.x;
         const bool valid = i < n;
+        if (RT_SHADE_PREFETCH) {  // the records of this block's next window, while this one computes
+            const uint32_t nxt = i + gridDim.x * kBlock;
+            if (nxt < n) { prefetch_l2(&cur.od0[nxt]); prefetch_l2(&cur.od1[nxt]); prefetch_l2(&cur.misc[nxt]); prefetch_l2(&hit[nxt]); }
+        }
         bool alive = false;
         V3 o = v3(0, 0, 0), d = v3(0, 0, 1), rayColor = v3(0, 0, 0);
         int32_t slotId = 0, hslot = -1, pixLocal = 0, batchFrame = 0;

@@ -458,7 +458,7 @@ int rth_add_displaced_sphere(rth_scene* s, int32_t n, const float center[3], flo
 }
 
 int rth_set_texture(rth_scene* s, int32_t slot, const uint8_t* px, int32_t w, int32_t h, int32_t ch) {
-    if (slot < 0 || slot >= RT_MAX_TEXTURES || !px || w <= 0 || h <= 0 || ch < 1 || ch > 4) {
+    if (!s || slot < 0 || slot >= RT_MAX_TEXTURES || !px || w <= 0 || h <= 0 || ch < 1 || ch > 4) {
         g_err = "bad texture";
         return RT_ERR_INVALID;
     }
@@ -667,16 +667,16 @@ int rth_write_png(const char* path, int32_t w, int32_t h, int32_t channels, cons
     FILE* f = fopen(path, "wb");
     if (!f) { g_err = std::string("rth_write_png: cannot open ") + path; return RT_ERR_INVALID; }
     static const uint8_t sig[8] = {0x89, 'P', 'N', 'G', 0x0d, 0x0a, 0x1a, 0x0a};
-    fwrite(sig, 1, 8, f);
+    bool wrote = fwrite(sig, 1, 8, f) == 8;
     auto chunk = [&](const char* type, const uint8_t* data, uint32_t len) {
         uint8_t hdr[8] = {(uint8_t)(len >> 24), (uint8_t)(len >> 16), (uint8_t)(len >> 8), (uint8_t)len,
                           (uint8_t)type[0], (uint8_t)type[1], (uint8_t)type[2], (uint8_t)type[3]};
-        fwrite(hdr, 1, 8, f);
-        if (len) fwrite(data, 1, len, f);
+        wrote = wrote && fwrite(hdr, 1, 8, f) == 8;
+        if (len) wrote = wrote && fwrite(data, 1, len, f) == len;
         uint32_t c = crc32buf(0, hdr + 4, 4);
         if (len) c = crc32buf(c, data, len);
         uint8_t cb[4] = {(uint8_t)(c >> 24), (uint8_t)(c >> 16), (uint8_t)(c >> 8), (uint8_t)c};
-        fwrite(cb, 1, 4, f);
+        wrote = wrote && fwrite(cb, 1, 4, f) == 4;
     };
     const uint8_t colorType = channels == 1 ? 0 : (channels == 3 ? 2 : 6);
     uint8_t ihdr[13] = {(uint8_t)(w >> 24), (uint8_t)(w >> 16), (uint8_t)(w >> 8), (uint8_t)w,
@@ -685,49 +685,82 @@ int rth_write_png(const char* path, int32_t w, int32_t h, int32_t channels, cons
     chunk("IHDR", ihdr, 13);
     chunk("IDAT", z.data(), (uint32_t)zlen);
     chunk("IEND", nullptr, 0);
-    fclose(f);
+    if (fclose(f) != 0 || !wrote) { g_err = std::string("rth_write_png: write failed: ") + path; return RT_ERR_INVALID; }
     return RT_OK;
 }
 
 // ------------------------------------------------------------------------------------------------ RTSC
 static const int64_t kMagic = 0x43535452;
 int rth_scene_save(const rth_scene* s, const char* path) {
+    if (!s || !path) { g_err = "rth_scene_save: NULL argument"; return RT_ERR_INVALID; }
     FILE* f = fopen(path, "wb");
     if (!f) { g_err = std::string("cannot open ") + path; return RT_ERR_INVALID; }
     const int ntex = rth_scene_texture_count(s);
     int64_t hdr[8] = {kMagic, (int64_t)s->tris.size(), (int64_t)s->mats.size(), 0, 0, ntex, 0, 0};
-    fwrite(hdr, 8, 8, f);
-    fwrite(s->tris.data(), sizeof(rt_triangle), s->tris.size(), f);
-    fwrite(s->mats.data(), sizeof(rt_material), s->mats.size(), f);
-    for (int i = 0; i < ntex; i++) {
+    bool ok = fwrite(hdr, 8, 8, f) == 8 &&
+              fwrite(s->tris.data(), sizeof(rt_triangle), s->tris.size(), f) == s->tris.size() &&
+              fwrite(s->mats.data(), sizeof(rt_material), s->mats.size(), f) == s->mats.size();
+    for (int i = 0; ok && i < ntex; i++) {
         int32_t th[4] = {s->tex[i].w, s->tex[i].h, s->tex[i].ch, 0};
-        fwrite(th, 4, 4, f);
-        fwrite(s->tex[i].px.data(), 1, s->tex[i].px.size(), f);
+        ok = fwrite(th, 4, 4, f) == 4 && fwrite(s->tex[i].px.data(), 1, s->tex[i].px.size(), f) == s->tex[i].px.size();
     }
-    fclose(f);
+    if (fclose(f) != 0 || !ok) { g_err = std::string("rth_scene_save: write failed: ") + path; return RT_ERR_INVALID; }
     return RT_OK;
 }
 int rth_scene_load(rth_scene* s, const char* path) {
+    // The header is untrusted: every count is checked against the file size before anything is resized, the file is
+    // read into temporaries, and the scene is only touched once the whole file has been accepted.
+    if (!s || !path) { g_err = "rth_scene_load: NULL argument"; return RT_ERR_INVALID; }
     FILE* f = fopen(path, "rb");
     if (!f) { g_err = std::string("cannot open ") + path; return RT_ERR_INVALID; }
-    int64_t hdr[8];
-    if (fread(hdr, 8, 8, f) != 8 || hdr[0] != kMagic) { fclose(f); g_err = "not an RTSC file"; return RT_ERR_INVALID; }
-    s->tris.resize((size_t)hdr[1]);
-    s->mats.resize((size_t)hdr[2]);
-    bool ok = fread(s->tris.data(), sizeof(rt_triangle), s->tris.size(), f) == s->tris.size() &&
-              fread(s->mats.data(), sizeof(rt_material), s->mats.size(), f) == s->mats.size();
-    ok = ok && fseek(f, (long)(hdr[3] * 48 + hdr[4] * 80), SEEK_CUR) == 0;
-    for (int i = 0; ok && i < hdr[5] && i < RT_MAX_TEXTURES; i++) {
-        int32_t th[4];
-        ok = fread(th, 4, 4, f) == 4;
-        if (!ok) break;
-        s->tex[i].w = th[0]; s->tex[i].h = th[1]; s->tex[i].ch = th[2];
-        s->tex[i].px.resize((size_t)th[0] * th[1] * th[2]);
-        ok = fread(s->tex[i].px.data(), 1, s->tex[i].px.size(), f) == s->tex[i].px.size();
+    struct Closer { FILE* f; ~Closer() { fclose(f); } } closer{f};
+    try {
+        if (fseek(f, 0, SEEK_END) != 0) { g_err = "cannot seek in RTSC file"; return RT_ERR_INVALID; }
+        const int64_t fileSize = (int64_t)ftell(f);
+        rewind(f);
+        int64_t hdr[8];
+        if (fread(hdr, 8, 8, f) != 8 || hdr[0] != kMagic) { g_err = "not an RTSC file"; return RT_ERR_INVALID; }
+        const int64_t nTris = hdr[1], nMats = hdr[2], nNodes = hdr[3], nSorted = hdr[4], nTex = hdr[5];
+        const int64_t lim = fileSize / 48 + 1;  // no section can hold more records than the file has bytes for
+        if (nTris < 0 || nMats < 0 || nNodes < 0 || nSorted < 0 || nTex < 0 || nTris > lim || nMats > lim || nNodes > lim ||
+            nSorted > lim || nTex > RT_MAX_TEXTURES ||
+            64 + nTris * (int64_t)sizeof(rt_triangle) + nMats * (int64_t)sizeof(rt_material) + nNodes * 48 + nSorted * 80 > fileSize) {
+            g_err = "RTSC header inconsistent with the file size";
+            return RT_ERR_INVALID;
+        }
+        std::vector<rt_triangle> tris((size_t)nTris);
+        std::vector<rt_material> mats((size_t)nMats);
+        bool ok = fread(tris.data(), sizeof(rt_triangle), tris.size(), f) == tris.size() &&
+                  fread(mats.data(), sizeof(rt_material), mats.size(), f) == mats.size();
+        ok = ok && fseek(f, (long)(nNodes * 48 + nSorted * 80), SEEK_CUR) == 0;
+        struct Tex { int32_t w = 0, h = 0, ch = 0; std::vector<uint8_t> px; } tex[RT_MAX_TEXTURES];
+        for (int i = 0; ok && i < nTex; i++) {
+            int32_t th[4];
+            ok = fread(th, 4, 4, f) == 4;
+            if (!ok) break;
+            if (th[0] <= 0 || th[1] <= 0 || th[2] < 1 || th[2] > 4 || (int64_t)th[0] * th[1] * th[2] > fileSize) {
+                g_err = "RTSC texture header out of range";
+                return RT_ERR_INVALID;
+            }
+            tex[i].w = th[0]; tex[i].h = th[1]; tex[i].ch = th[2];
+            tex[i].px.resize((size_t)th[0] * th[1] * th[2]);
+            ok = fread(tex[i].px.data(), 1, tex[i].px.size(), f) == tex[i].px.size();
+        }
+        if (!ok) { g_err = "truncated RTSC file"; return RT_ERR_INVALID; }
+        s->tris.swap(tris);
+        s->mats.swap(mats);
+        for (int i = 0; i < nTex; i++) {
+            s->tex[i].w = tex[i].w; s->tex[i].h = tex[i].h; s->tex[i].ch = tex[i].ch;
+            s->tex[i].px.swap(tex[i].px);
+        }
+        return RT_OK;
+    } catch (const std::bad_alloc&) {
+        g_err = "rth_scene_load: out of memory";
+        return RT_ERR_OOM;
+    } catch (const std::exception& e) {
+        g_err = std::string("rth_scene_load: ") + e.what();
+        return RT_ERR_INVALID;
     }
-    fclose(f);
-    if (!ok) { g_err = "truncated RTSC file"; return RT_ERR_INVALID; }
-    return RT_OK;
 }
 
 }  // extern "C"

@@ -135,6 +135,37 @@ def test_named_scenes_and_png(tmp_path):
     assert np.array_equal(s2.textures[0], s.textures[0])
 
 
+def test_scene_load_rejects_hostile_files(tmp_path):
+    """rth_scene_load trusts nothing in the header: negative / huge counts, a texture header out of range and a
+    truncated file are refused with an error (no exception crosses the C boundary) and leave the scene untouched."""
+    import struct
+    s = rt.scene_textured_sphere(n_quads=4, container="cornell", tex_size=8)
+    good = str(tmp_path / "good.rtsc")
+    s.save(good)
+    blob = open(good, "rb").read()
+    magic = struct.unpack_from("<q", blob, 0)[0]
+
+    def attempt(data):
+        path = str(tmp_path / "bad.rtsc")
+        open(path, "wb").write(data)
+        t = rt.scene_classic_cornell()
+        before = t.triangles.tobytes()
+        with pytest.raises(rt.BackendError):
+            t.load(path)
+        assert t.triangles.tobytes() == before    # the scene is only replaced by a file that was accepted whole
+
+    attempt(blob[: len(blob) // 2])                                               # truncated
+    attempt(struct.pack("<8q", magic, -5, 7, 0, 0, 1, 0, 0) + blob[64:])           # negative triangle count
+    attempt(struct.pack("<8q", magic, 1 << 60, 7, 0, 0, 1, 0, 0) + blob[64:])      # absurd triangle count
+    attempt(struct.pack("<8q", magic, 0, 0, 1 << 40, 0, 0, 0, 0))                  # absurd node section
+    attempt(struct.pack("<8q", magic, 0, 0, 0, 0, 99, 0, 0))                       # more textures than slots
+    attempt(struct.pack("<8q", magic, 0, 0, 0, 0, 1, 0, 0) + struct.pack("<4i", -4, 8, 3, 0))   # negative texture width
+    attempt(struct.pack("<8q", magic, 0, 0, 0, 0, 1, 0, 0) + struct.pack("<4i", 8, 8, 9, 0))    # 9 channels
+    attempt(b"not an rtsc file at all, just some bytes that are long enough to hold a header........")
+    with pytest.raises(rt.BackendError):
+        rt.write_png(str(tmp_path / "no_such_dir" / "x.png"), np.zeros((2, 2, 3), np.uint8))
+
+
 # ------------------------------------------------------------------------------------------------ N > 1 on gloo
 _WORKER = r'''
 import importlib, os, sys
