@@ -267,12 +267,12 @@ __global__ void __launch_bounds__(kBlock) k_raygen(const __grid_constant__ Frame
 // The closest-hit rule (min dst, then lowest original index) makes the result independent of the
 // order in which lanes, nodes and triangles are visited, so the restructuring changes no bit.
 constexpr int kExtBlock = 128;
-// experiment switches (tools/build_variant.sh): software prefetch of the streaming path records into L2
+// Software prefetch of the streaming ray records into L2: at a refill every lane asks for the record a lane of this
+// grid will claim about one refill generation later.  Config 2: 5859 vs 5806 Mrays/s (+0.9 %, twice: alone and
+// together with a prefetch of k_shade's next window, which by itself changed nothing and is not kept);
+// profiles/r2_prefetch_ab.txt.
 #ifndef RT_EXT_PREFETCH
-#define RT_EXT_PREFETCH 0
-#endif
-#ifndef RT_SHADE_PREFETCH
-#define RT_SHADE_PREFETCH 0
+#define RT_EXT_PREFETCH 1
 #endif
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 #ifndef RT_EXT_MIN_BLOCKS
@@ -765,10 +765,6 @@ __global__ void __launch_bounds__(kBlock, RT_SHADE_MIN_BLOCKS) k_shade(const __g
     for (uint32_t base = blockIdx.x * kBlock; base < n; base += gridDim.x * kBlock) {
         const uint32_t i = base + threadIdx.x;
         const bool valid = i < n;
-        if (RT_SHADE_PREFETCH) {  // the records of this block's next window, while this one computes
-            const uint32_t nxt = i + gridDim.x * kBlock;
-            if (nxt < n) { prefetch_l2(&cur.od0[nxt]); prefetch_l2(&cur.od1[nxt]); prefetch_l2(&cur.misc[nxt]); prefetch_l2(&hit[nxt]); }
-        }
         bool alive = false;
         V3 o = v3(0, 0, 0), d = v3(0, 0, 1), rayColor = v3(0, 0, 0);
         int32_t slotId = 0, hslot = -1, pixLocal = 0, batchFrame = 0;

@@ -35,11 +35,11 @@ for rep in sys.argv[1:]:
     for i, r in enumerate(data):
         st = []
         for h in hdr:
-            if h.startswith(STALLS) and h.endswith("_per_warp_active.pct"):
+            if h.startswith(STALLS) and h.endswith("_per_issue_active.ratio"):
                 try:
-                    st.append((float(r[col[h]]), h[len(STALLS):-len("_per_warp_active.pct")]))
+                    st.append((float(r[col[h]]), h[len(STALLS):-len("_per_issue_active.ratio")]))
                 except ValueError:
                     pass
         st.sort(reverse=True)
-        print(f"stalls launch {i} ({names[i]}): " + ", ".join(f"{n} {v:.1f}%" for v, n in st[:8]))
+        print(f"warps stalled per issue, launch {i} ({names[i]}): " + ", ".join(f"{n} {v:.2f}" for v, n in st[:8]))
     print()
