@@ -571,8 +571,7 @@ def side_block(R, rt, name, frames, steps, warmup, ceil):
     m = R.timed(be, u, frames, steps, warmup)
     c = m["counters"]
     shot = be.screenshot(u, frames)
-    gate = parity_gate(rt, be, scene, name, shot, frames, 1) if WORKLOADS[name]["scene"] != "big_sphere" else \
-        {"screenshot_crc": int(zlib.crc32(shot.tobytes()) & 0xffffffff)}
+    gate = parity_gate(rt, be, scene, name, shot, frames, 1)
     be.close()
     ci = R.instrumented(scene, u)
     roof = extend_roofline(c, ci, ceil, name, c["bvh_bytes"], m["ms_total"], None, c["bvh_width"])
