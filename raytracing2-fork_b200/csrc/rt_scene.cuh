@@ -192,14 +192,15 @@ constexpr float kMissT = 1e38f;
 
 // compute.glsl:302-340 on the precomputed (a, e0, e1, N).  Returns true on a hit and the same
 // dst/u/v bits the reference expression order produces.
+// tMax: a candidate farther than the best hit so far cannot win; leaving before the barycentrics changes no result.
 __device__ __forceinline__ bool ray_triangle(V3 o, V3 d, V3 a, V3 e0, V3 e1, V3 N, float& dst,
-                                             float& u, float& v) {
+                                             float& u, float& v, float tMax = 3.4e38f) {
     const float det = -dot(d, N);
     if ((det < 1e-10f && det > -1e-10f) || det < 0.0f) return false;
     const float invDet = 1.0f / det;
     const V3 ao = o - a;
     dst = dot(ao, N) * invDet;
-    if (dst <= 1e-6f) return false;
+    if (dst <= 1e-6f || dst > tMax) return false;
     const V3 dao = cross(d, ao);
     u = -dot(e1, dao) * invDet;
     v = dot(e0, dao) * invDet;

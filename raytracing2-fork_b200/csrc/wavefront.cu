@@ -275,6 +275,16 @@ constexpr int kExtBlock = 128;
 #define RT_EXT_PREFETCH 1
 #endif
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+#ifndef RT_EXT_TMAX
+#define RT_EXT_TMAX 1   // the triangle test leaves before the barycentrics when dst > best
+#endif
+#ifndef RT_EXT_LAZY_ORIG
+#define RT_EXT_LAZY_ORIG 1
+#endif
+// Rays claimed from the queue per atomicAdd on the shared cursor (0 = one atomic per refill, round 1's scheme).
+#ifndef RT_EXT_CLAIM
+#define RT_EXT_CLAIM 128
+#endif
 #ifndef RT_EXT_MIN_BLOCKS
 #define RT_EXT_MIN_BLOCKS 9   // 56 registers: nine resident blocks per SM (ten at 48 registers measured 0.8 % slower, eight slower too)
 #endif
@@ -409,6 +419,11 @@ __global__ void __launch_bounds__(kExtBlock, RT_EXT_MIN_BLOCKS) k_extend(const _
     const float kWiden = WIDEN ? kWidenFar : 1.0f;  // x * 1.0f folds away
 
     __shared__ int2 shStack[kShStack][kExtBlock];
+#if RT_EXT_CLAIM > 0
+    __shared__ uint32_t sClaim[kExtBlock / 32][4];  // per warp: next, end of its private range; queue exhausted
+    if ((threadIdx.x & 31u) == 0u) { sClaim[threadIdx.x >> 5][0] = 0u; sClaim[threadIdx.x >> 5][1] = 0u; sClaim[threadIdx.x >> 5][2] = 0u; }
+    __syncwarp();
+#endif
     __shared__ uint4 sTop[TOP ? 4 * kTopNodes : 1];
     if (TOP) {
         const int have = min(4 * kTopNodes, 4 * sc.num_nodes4);
@@ -440,13 +455,25 @@ __global__ void __launch_bounds__(kExtBlock, RT_EXT_MIN_BLOCKS) k_extend(const _
         const TriGeom tg = load_tri(sc, s);
         if (COUNT) tests++;
         float dst, u, v;
-        if (ray_triangle(r.o, r.d, tg.a, tg.e0, tg.e1, tg.N, dst, u, v)) {
+        if (ray_triangle(r.o, r.d, tg.a, tg.e0, tg.e1, tg.N, dst, u, v, RT_EXT_TMAX ? r.bestT : 3.4e38f)) {
+#if RT_EXT_LAZY_ORIG
+            // the original indices are needed only to break an exact tie in dst: fetch them then, not for every
+            // candidate (the dependent 4-byte gather was 3.4 % of k_extend's stall samples)
+            if (dst <= r.bestT && dst < kMissT) {
+                bool take = dst < r.bestT;
+                if (!take) take = __ldg(&sc.tri_orig[s]) < __ldg(&sc.tri_orig[bestSlot]);  // bestT < kMissT: bestSlot >= 0
+                if (take) {
+                    r.bestT = dst; bestU = u; bestV = v; bestSlot = s;
+                }
+            }
+#else
             if (dst <= r.bestT && dst < kMissT) {
                 const int32_t orig = __ldg(&sc.tri_orig[s]);
                 if (dst < r.bestT || orig < bestOrig) {
                     r.bestT = dst; bestU = u; bestV = v; bestSlot = s; bestOrig = orig;
                 }
             }
+#endif
         }
     };
     auto test_leaf = [&](int32_t code) {
@@ -518,6 +545,66 @@ __global__ void __launch_bounds__(kExtBlock, RT_EXT_MIN_BLOCKS) k_extend(const _
         }
         // ---- refill idle lanes from the queue
         uint32_t idle = __ballot_sync(FULL, node == kIdle);
+#if RT_EXT_CLAIM > 0
+        if (!exhausted && ((int)__popc(idle) >= tune.refill || idle == FULL)) {
+            // The warp owns a private range [next, end) of the queue, claimed RT_EXT_CLAIM rays at a time: one atomic on
+            // the shared cursor per chunk instead of one per refill, and a refill out of the private range waits for no
+            // atomic at all.  The leftover of a range is handed out before the fresh chunk, so no ray is skipped.
+            uint32_t* const cl = sClaim[threadIdx.x >> 5];
+            const uint32_t next = cl[0], end = cl[1], gdone = cl[2];
+            const uint32_t want = __popc(idle);
+            const uint32_t avail = end - next;
+            const bool fresh = avail < want && gdone == 0u;  // warp-uniform
+            uint32_t fbase = 0, fend = 0;
+            if (fresh) {
+                const int leader = __ffs(idle) - 1;
+                if ((int)lane == leader) fbase = atomicAdd(cursor, (uint32_t)RT_EXT_CLAIM);
+                fbase = __shfl_sync(FULL, fbase, leader);
+                fbase = min(fbase, n);
+                fend = min(fbase + (uint32_t)RT_EXT_CLAIM, n);
+                if (RT_EXT_PREFETCH) {  // the chunk a warp of this grid will claim about one generation from now
+                    const uint32_t ahead = fbase + gridDim.x * (kExtBlock / 32) * (uint32_t)RT_EXT_CLAIM + 8u * (lane & 15u);
+                    if (ahead < n && 8u * (lane & 15u) < (uint32_t)RT_EXT_CLAIM) prefetch_l2(lane < 16u ? &cur.od0[ahead] : &cur.od1[ahead]);
+                }
+            }
+            if (node == kIdle) {
+                const uint32_t rank = __popc(idle & ltMask);
+                uint32_t i = next + rank;
+                bool have = rank < avail;
+                if (!have && fresh) {
+                    i = fbase + (rank - avail);
+                    have = i < fend;
+                }
+                if (have) {
+                    const float4 a = cur.od0[i];
+                    const float4 b = cur.od1[i];
+                    ray = i;
+                    r.o = v3(a.x, a.y, a.z);
+                    r.d = v3(a.w, b.x, b.y);
+                    r.g = make_grid_ray(sc, r.o, r.d);
+                    r.bestT = kMissT; bestU = 0.0f; bestV = 0.0f; bestSlot = -1; bestOrig = 0x7fffffff;
+                    sp = 0;
+                    post = kNoLeaf;
+                    node = sc.root_is_leaf ? pack_leaf(0, sc.num_tris) : 0;
+                    postpone();
+                }
+            }
+            uint32_t nnext, nend, ndone = gdone;
+            if (fresh) {
+                nnext = min(fbase + (want - avail), fend);
+                nend = fend;
+                if (fend >= n) ndone = 1u;
+            } else {
+                nnext = next + min(want, avail);
+                nend = end;
+            }
+            __syncwarp();
+            if (lane == 0) { cl[0] = nnext; cl[1] = nend; cl[2] = ndone; }
+            __syncwarp();
+            if (ndone != 0u && nnext == nend) exhausted = true;
+            idle = __ballot_sync(FULL, node == kIdle);
+        }
+#else
         if (!exhausted && ((int)__popc(idle) >= tune.refill || idle == FULL)) {
             uint32_t base = 0;
             const int leader = __ffs(idle) - 1;
@@ -547,6 +634,7 @@ __global__ void __launch_bounds__(kExtBlock, RT_EXT_MIN_BLOCKS) k_extend(const _
             if (base + want >= n) exhausted = true;
             idle = __ballot_sync(FULL, node == kIdle);
         }
+#endif
         if (idle == FULL) {
             if (exhausted) break;
             continue;
@@ -748,10 +836,14 @@ __device__ __forceinline__ BounceRandoms bounce_randoms(Rng<1>& rng, bool needDi
 // texture fetch diverges.  What is kept from that work: the random numbers of a bounce are drawn by the converged
 // warp, and a warp whose paths all end (miss, light, unknown material) draws none.
 // One bounce of S:481-560 for every live path.  `bounce` is the 0-based index of this segment.
+// Measured and not kept (profiles/r2_final_ab.txt): survivors appended with one atomicAdd per BLOCK window (warp counts
+// scanned in shared memory between two barriers) instead of one per warp: config 2 5604 vs 5854 Mrays/s (-4.3 %),
+// config 4 4219 vs 4280 — the atomic's cost is its latency, not the number of atomics, and a barrier adds the wait for
+// the block's slowest warp on top.  What ships is the deferred append below.
 #ifndef RT_SHADE_MIN_BLOCKS
 #define RT_SHADE_MIN_BLOCKS 4   // 64 registers; 5 blocks (48 registers, 358 B of spills) -15 %, 6 blocks -16 % (profiles/r2_leafmerge_shadeocc_ab.txt)
 #endif
-template <int MODE>
+template <int MODE, bool DEFER>
 __global__ void __launch_bounds__(kBlock, RT_SHADE_MIN_BLOCKS) k_shade(const __grid_constant__ SceneView sc,
                                                   const __grid_constant__ FrameParams fp, PathArrays cur,
                                                   PathArrays next, const float4* __restrict__ hit,
@@ -759,6 +851,8 @@ __global__ void __launch_bounds__(kBlock, RT_SHADE_MIN_BLOCKS) k_shade(const __g
                                                   const uint32_t* __restrict__ countIn,
                                                   uint32_t* __restrict__ countOut, int bounce) {
     __shared__ CoopSlot sCoop[kBlock / 32][kCoopOwners];  // stage 2 of bounce_randoms: keys handed to the warp
+    __shared__ float4 sStage[3][DEFER ? kBlock : 1];  // a lane's surviving path while the warp's queue reservation is in flight
+    uint32_t pendMask = 0u, pendRaw = 0u;             // survivors of the previous window; the leader lane's atomicAdd result
     const uint32_t n = *countIn;
     const uint32_t lane = threadIdx.x & 31u;
     constexpr uint32_t FULL = 0xffffffffu;
@@ -895,18 +989,54 @@ __global__ void __launch_bounds__(kBlock, RT_SHADE_MIN_BLOCKS) k_shade(const __g
         }
         // compaction: the survivors of this warp take consecutive places in the next queue
         const uint32_t mask = __ballot_sync(FULL, alive);
-        uint32_t basePos = 0;
-        if (mask) {
-            const int leader = __ffs(mask) - 1;
-            if ((int)lane == leader) basePos = atomicAdd(countOut, (uint32_t)__popc(mask));
-            basePos = __shfl_sync(FULL, basePos, leader);
+        if (DEFER) {
+            // Deferred append: the warp's atomicAdd on the queue counter takes microseconds to return (ncu, v19: 41.6 %
+            // of k_shade's stall samples at bounce 0 of config 2 and 44 % at every bounce of config 4 sat on the shuffle
+            // that broadcasts its result).  The survivors wait in shared memory — every lane in its OWN slot, so no
+            // synchronisation is needed — while the reservation is in flight, and are written to the queue at the end
+            // of the NEXT window, one whole iteration later.
+            if (pendMask != 0u) {
+                const uint32_t b0 = __shfl_sync(FULL, pendRaw, __ffs(pendMask) - 1);
+                if ((pendMask >> lane) & 1u) {
+                    const uint32_t pos = b0 + __popc(pendMask & ((1u << lane) - 1u));
+                    next.od0[pos] = sStage[0][threadIdx.x];
+                    next.od1[pos] = sStage[1][threadIdx.x];
+                    next.misc[pos] = sStage[2][threadIdx.x];
+                }
+            }
+            pendMask = mask;
+            if (mask) {
+                if ((int)lane == __ffs(mask) - 1) pendRaw = atomicAdd(countOut, (uint32_t)__popc(mask));
+                if (alive) {
+                    sStage[0][threadIdx.x] = make_float4(o.x, o.y, o.z, d.x);
+                    sStage[1][threadIdx.x] = make_float4(d.y, d.z, rayColor.x, rayColor.y);
+                    sStage[2][threadIdx.x] = make_float4(rayColor.z, __int_as_float(slotId), __uint_as_float(carry),
+                                                         __uint_as_float(flags));
+                }
+            }
+        } else {
+            uint32_t basePos = 0;
+            if (mask) {
+                const int leader = __ffs(mask) - 1;
+                if ((int)lane == leader) basePos = atomicAdd(countOut, (uint32_t)__popc(mask));
+                basePos = __shfl_sync(FULL, basePos, leader);
+            }
+            const uint32_t pos = basePos + __popc(mask & ((1u << lane) - 1u));
+            if (alive) {
+                next.od0[pos] = make_float4(o.x, o.y, o.z, d.x);
+                next.od1[pos] = make_float4(d.y, d.z, rayColor.x, rayColor.y);
+                next.misc[pos] = make_float4(rayColor.z, __int_as_float(slotId), __uint_as_float(carry),
+                                             __uint_as_float(flags));
+            }
         }
-        const uint32_t pos = basePos + __popc(mask & ((1u << lane) - 1u));
-        if (alive) {
-            next.od0[pos] = make_float4(o.x, o.y, o.z, d.x);
-            next.od1[pos] = make_float4(d.y, d.z, rayColor.x, rayColor.y);
-            next.misc[pos] = make_float4(rayColor.z, __int_as_float(slotId), __uint_as_float(carry),
-                                         __uint_as_float(flags));
+    }
+    if (DEFER && pendMask != 0u) {  // the last window of this warp
+        const uint32_t b0 = __shfl_sync(FULL, pendRaw, __ffs(pendMask) - 1);
+        if ((pendMask >> lane) & 1u) {
+            const uint32_t pos = b0 + __popc(pendMask & ((1u << lane) - 1u));
+            next.od0[pos] = sStage[0][threadIdx.x];
+            next.od1[pos] = sStage[1][threadIdx.x];
+            next.misc[pos] = sStage[2][threadIdx.x];
         }
     }
 }
@@ -1270,12 +1400,22 @@ cudaError_t wf_render_batch(const Launcher& L, const SceneView& sc, const WaveBu
         }
         {
             Timed t(L, 1);
-            if (L.rng_mode == RT_RNG_REF_PCG)
-                k_shade<0><<<grid, kBlock, 0, L.st>>>(sc, fp, a, b, wb.hit, wb.contrib, wb.pix_rng, wb.counts + bounce,
-                                                      wb.counts + bounce + 1, bounce);
-            else
-                k_shade<1><<<grid, kBlock, 0, L.st>>>(sc, fp, a, b, wb.hit, wb.contrib, wb.pix_rng, wb.counts + bounce,
-                                                      wb.counts + bounce + 1, bounce);
+            // Deferred append (see k_shade): 0 never, 1 at bounce 0 only, 2 at every bounce, 3 (default) at bounce 0 and,
+            // when the scene has no textures, at every bounce.  Measured on B200 (profiles/r2_final_ab.txt): bounce 0 is
+            // latency-bound everywhere (config 2: +1.5 % from deferring it alone); the later bounces of the textured
+            // config-2 scene are issue-bound (66 % issue-active, 17.8 lanes per instruction) and LOSE 0.8-2.4 % to the
+            // staging, those of the untextured 10 M-triangle scene wait on the atomic like bounce 0 does (34 %
+            // issue-active, 44 % of the stall samples) and gain 3.3-9.4 % depending on the box.
+            const bool defer = L.shade_defer == 2 || (L.shade_defer == 1 && bounce == 0) ||
+                               (L.shade_defer >= 3 && (bounce == 0 || fp.u.numTextures <= 0));
+#define RT_SHADE(M, D) k_shade<M, D><<<grid, kBlock, 0, L.st>>>(sc, fp, a, b, wb.hit, wb.contrib, wb.pix_rng, wb.counts + bounce, \
+                                                              wb.counts + bounce + 1, bounce)
+            if (L.rng_mode == RT_RNG_REF_PCG) {
+                if (defer) RT_SHADE(0, true); else RT_SHADE(0, false);
+            } else {
+                if (defer) RT_SHADE(1, true); else RT_SHADE(1, false);
+            }
+#undef RT_SHADE
             (*L.kernel_launches)++;
         }
         PathArrays tmp = a;

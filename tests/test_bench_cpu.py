@@ -101,3 +101,17 @@ def test_reference_arm_prints_the_contract_line():
     assert d["cpu_baseline"]["kind"] in ("reference", "port") and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"] == {"value": d["value"], "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert d["config"]["name"] == "config1" and "workload" in d["config"]
+
+
+def test_microbench_library_is_built_by_build():
+    """bench.py's `ceilings` block (the L2 / HBM gather and FP32-issue rates the roofline is measured against) needs
+    tools/libmicrobench.so; __graft_entry__.build() must compile it, and it must export what bench.microbench binds."""
+    import ctypes
+    path = os.path.join(REPO, "tools", "libmicrobench.so")
+    if not os.path.exists(path):
+        subprocess.check_call(["make", "-C", os.path.join(REPO, "tools"), "all"])
+    src = open(os.path.join(REPO, "__graft_entry__.py")).read()
+    assert '"tools"), "all"' in src, "build() does not compile tools/libmicrobench.so"
+    L = ctypes.CDLL(path)
+    for sym in ("mb_gather_gbs", "mb_issue_tops", "mb_stream_gbs"):
+        assert hasattr(L, sym), sym

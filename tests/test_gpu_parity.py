@@ -658,11 +658,12 @@ def test_real_asset_robot_if_generated():
 # ------------------------------------------------------------------------------------------------ round 2
 @pytest.mark.parametrize("env", [{"RT_EXT_TOP": "1"}, {"RT_HOOKS": "thread"}, {"RT_BVH_WIDTH": "2"}, {"RT_MAX_PATHS_MI": "1"},
                                  {"RT_BVH_BUILDER": "lbvh"}, {"RT_BVH_BUILDER": "lbvh", "RT_BVH_WIDTH": "2"},
-                                 {"RT_EXT_WIDEN": "1"}])
+                                 {"RT_EXT_WIDEN": "1"}, {"RT_SHADE_DEFER": "0"}, {"RT_SHADE_DEFER": "2"}])
 @pytest.mark.parametrize("rng_mode", [rt.RNG_REF_PCG, rt.RNG_PHILOX])
 def test_kernel_variants_change_no_bit(monkeypatch, env, rng_mode):
     """The shared-memory top of the tree, the per-thread hooks, the binary tree, the Karras builder, the always-widened
-    slab test and a tiny path budget only reorder or re-route work: frame, first-hit map and random rays must equal
+    slab test, k_shade's deferred queue append (never / at every bounce; the default defers bounce 0) and a tiny path
+    budget only reorder or re-route work: frame, first-hit map and random rays must equal
     the oracle bit for bit under every switch (the defaults are covered by every other test)."""
     for k, v in env.items():
         monkeypatch.setenv(k, v)
@@ -801,4 +802,21 @@ def test_duplicate_geometry_builds(classic):
     a = be.trace_rays(o, d)
     b = orc.trace_rays(o, d, use_bvh=False)
     assert np.array_equal(a[0], b[0]) and np.array_equal(bits(a[1]), bits(b[1]))
+    be.close()
+
+
+@pytest.mark.gpu
+def test_ray_counts_around_the_claim_size(sphere_box):
+    """k_extend's warps claim the ray queue 128 rays at a time and hand the leftover of a claim out before the next
+    one: every ray must be traced exactly once whatever the queue length is (1 ray, one short of / exactly / one past a
+    claim, a few claims plus a ragged tail), ids / distances / barycentrics equal to the exhaustive oracle."""
+    scene, orc = sphere_box
+    be = backend(scene)
+    o, d = random_rays(4200, 77, -4.0, 4.0)
+    ref = orc.trace_rays(o, d, use_bvh=False)
+    for n in (1, 31, 32, 127, 128, 129, 255, 256, 257, 1000, 4096, 4097, 4200):
+        got = be.trace_rays(o[:n], d[:n])
+        assert np.array_equal(got[0], ref[0][:n]), n
+        for k in (1, 2, 3):
+            assert np.array_equal(bits(got[k]), bits(ref[k][:n])), (n, k)
     be.close()
