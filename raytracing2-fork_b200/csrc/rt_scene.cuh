@@ -58,8 +58,16 @@ constexpr float kGuardCells = 0.125f;
 
 // 256-bit read-only global load (sm_100a: LDG.E.ENL2.256.CONSTANT): one instruction, one L1TEX
 // wavefront per lane for 32 bytes, where four 128-bit loads of a 64-byte record would cost four.
+// L1 eviction-priority hints of the two gathers of k_extend (PTX `.L1::evict_last` / `.L1::evict_first` /
+// `.L1::no_allocate`), empty by default; measured in profiles/r2_final_ab.txt.
+#ifndef RT_NODE_HINT
+#define RT_NODE_HINT ""
+#endif
+#ifndef RT_TRI_HINT
+#define RT_TRI_HINT ""
+#endif
 __device__ __forceinline__ void ldg256u(const void* p, uint32_t (&v)[8]) {
-    asm volatile("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+    asm volatile("ld.global.nc" RT_NODE_HINT ".v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                  : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
                  : "l"(p));
 }
@@ -172,10 +180,13 @@ struct TriGeom {
 };
 __device__ __forceinline__ TriGeom load_tri(const SceneView& sc, int32_t s) {
     float g[8];
-    asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+    asm volatile("ld.global.nc" RT_TRI_HINT ".v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                  : "=f"(g[0]), "=f"(g[1]), "=f"(g[2]), "=f"(g[3]), "=f"(g[4]), "=f"(g[5]), "=f"(g[6]), "=f"(g[7])
                  : "l"(sc.tri_geom + 4 * s));
-    const float4 h = __ldg(sc.tri_geom + 4 * s + 2);
+    float4 h;
+    asm volatile("ld.global.nc" RT_TRI_HINT ".v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(h.x), "=f"(h.y), "=f"(h.z), "=f"(h.w)
+                 : "l"(sc.tri_geom + 4 * s + 2));
     TriGeom t;
     t.a = v3(g[0], g[1], g[2]);
     t.e0 = v3(g[3], g[4], g[5]);

@@ -267,10 +267,12 @@ __global__ void __launch_bounds__(kBlock) k_raygen(const __grid_constant__ Frame
 // The closest-hit rule (min dst, then lowest original index) makes the result independent of the
 // order in which lanes, nodes and triangles are visited, so the restructuring changes no bit.
 constexpr int kExtBlock = 128;
-// Software prefetch of the streaming ray records into L2: at a refill every lane asks for the record a lane of this
-// grid will claim about one refill generation later.  Config 2: 5859 vs 5806 Mrays/s (+0.9 %, twice: alone and
-// together with a prefetch of k_shade's next window, which by itself changed nothing and is not kept);
-// profiles/r2_prefetch_ab.txt.
+// Software prefetch of the streaming ray records.  Without chunked claims (RT_EXT_CLAIM = 0) every lane asks, at a
+// refill, for the record a lane of this grid will claim about one refill generation later: config 2, 5859 vs 5806
+// Mrays/s (+0.9 %; profiles/r2_prefetch_ab.txt).  With chunked claims the warp knows its next records exactly:
+// 1 = the head of the private range into L2 at every refill, 3 = the same into L1, 2 = the whole chunk that some warp
+// will claim one generation ahead (it is evicted again before it is used often enough to cost 8 B of DRAM traffic per
+// segment: ncu, profiles/r2_traffic_*.csv of the v20 capture), 0 = none.
 #ifndef RT_EXT_PREFETCH
 #define RT_EXT_PREFETCH 1
 #endif
@@ -562,7 +564,7 @@ __global__ void __launch_bounds__(kExtBlock, RT_EXT_MIN_BLOCKS) k_extend(const _
                 fbase = __shfl_sync(FULL, fbase, leader);
                 fbase = min(fbase, n);
                 fend = min(fbase + (uint32_t)RT_EXT_CLAIM, n);
-                if (RT_EXT_PREFETCH) {  // the chunk a warp of this grid will claim about one generation from now
+                if (RT_EXT_PREFETCH == 2) {  // the chunk a warp of this grid will claim about one generation from now
                     const uint32_t ahead = fbase + gridDim.x * (kExtBlock / 32) * (uint32_t)RT_EXT_CLAIM + 8u * (lane & 15u);
                     if (ahead < n && 8u * (lane & 15u) < (uint32_t)RT_EXT_CLAIM) prefetch_l2(lane < 16u ? &cur.od0[ahead] : &cur.od1[ahead]);
                 }
@@ -598,6 +600,16 @@ __global__ void __launch_bounds__(kExtBlock, RT_EXT_MIN_BLOCKS) k_extend(const _
                 nnext = next + min(want, avail);
                 nend = end;
             }
+            if ((RT_EXT_PREFETCH == 1 || RT_EXT_PREFETCH == 3) && lane < 10u) {
+                // the records this warp takes at its NEXT refill are known exactly: the head of its private range
+                // (five 128-byte lines of each array cover 32 records wherever the range starts)
+                const uint32_t p = nnext + 8u * (lane < 5u ? lane : lane - 5u);
+                const void* q = lane < 5u ? (const void*)&cur.od0[p] : (const void*)&cur.od1[p];
+                if (p < nend) {
+                    if (RT_EXT_PREFETCH == 3) asm volatile("prefetch.global.L1 [%0];" ::"l"(q));
+                    else prefetch_l2(q);
+                }
+            }
             __syncwarp();
             if (lane == 0) { cl[0] = nnext; cl[1] = nend; cl[2] = ndone; }
             __syncwarp();
@@ -613,7 +625,7 @@ __global__ void __launch_bounds__(kExtBlock, RT_EXT_MIN_BLOCKS) k_extend(const _
             base = __shfl_sync(FULL, base, leader);
             if (node == kIdle) {
                 const uint32_t i = base + __popc(idle & ltMask);
-                if (RT_EXT_PREFETCH) {  // the record a lane of this grid will claim about one refill generation from now
+                if (RT_EXT_PREFETCH != 0) {  // the record a lane of this grid will claim about one refill generation from now
                     const uint32_t ahead = i + gridDim.x * kExtBlock;
                     if (ahead < n) { prefetch_l2(&cur.od0[ahead]); prefetch_l2(&cur.od1[ahead]); }
                 }
