@@ -162,6 +162,12 @@ __device__ __forceinline__ uint32_t quantize8(float c) {  // float → unorm8 of
 __device__ __forceinline__ float u32_to_unit(uint32_t r) {
     return (float)r / 4294967296.0f;  // compute.glsl:153 (the literal is a float: 2^32)
 }
+// random() * 2 - 1 (compute.glsl:177-179) straight from the 32-bit draw: float(r) / 2^32 and the doubling are exact
+// scalings by powers of two, so the only rounding of `u32_to_unit(r) * 2.0f - 1.0f` is that of the subtraction, and
+// fma(float(r), 2^-31, -1) rounds the same exact value once — identical bits, two instructions instead of four.
+__device__ __forceinline__ float u32_to_signed_unit(uint32_t r) {
+    return __fmaf_rn((float)r, 4.656612873077392578125e-10f, -1.0f);
+}
 __device__ __forceinline__ float pcg_next(uint32_t& state) {  // compute.glsl:148-154
     state = state * 747796405u + 2891336453u;
     uint32_t result = ((state >> ((state >> 28u) + 4u)) ^ state) * 277803737u;

@@ -318,3 +318,24 @@ def test_rejection_test_without_sqrt():
     rnd = rng.uniform(0.0, 3.0, 2_000_000).astype(np.float32)
     for x in (near, rnd):
         assert np.array_equal(np.sqrt(x, dtype=np.float32) < np.float32(1.0), x < np.float32(1.0))
+
+
+def test_signed_unit_draw_by_one_fma():
+    """k_shade turns a 32-bit Philox word into a candidate component `random() * 2 - 1` (compute.glsl:153, 177-179) as
+    fma(float(r), 2^-31, -1) instead of ((float(r) / 2^32) * 2) - 1.  float(r) / 2^32 and the doubling are exact scalings
+    by powers of two, so both forms round the same exact value once.  Checked on every fifth binary32 in [1, 2^32] — a
+    superset of the values float(r) can take — and on the edges.  The fma is emulated in binary64: x * 2^-31 is exact
+    there, and the subtraction is exact for x >= 4 (the result then needs at most 53 bits); for x < 4 the result lies
+    within 2^-29 of -1, far from any binary32 rounding boundary, so the second rounding cannot change it."""
+    lo, hi = int(np.float32(1.0).view(np.uint32)), int(np.float32(4294967296.0).view(np.uint32))
+    two31 = np.float64(2.0) ** -31
+    for start in range(lo, hi + 1, 5 * (1 << 22)):
+        bits = np.arange(start, min(start + 5 * (1 << 22), hi + 1), 5, dtype=np.uint32)
+        x = bits.view(np.float32)
+        old = (x / np.float32(4294967296.0)) * np.float32(2.0) - np.float32(1.0)
+        new = (x.astype(np.float64) * two31 - 1.0).astype(np.float32)
+        assert np.array_equal(old.view(np.uint32), new.view(np.uint32))
+    edge = np.array([0.0, 1.0, 2.0, 3.0, 2147483648.0, 4294967040.0, 4294967296.0], np.float32)
+    old = (edge / np.float32(4294967296.0)) * np.float32(2.0) - np.float32(1.0)
+    new = (edge.astype(np.float64) * two31 - 1.0).astype(np.float32)
+    assert np.array_equal(old.view(np.uint32), new.view(np.uint32))
