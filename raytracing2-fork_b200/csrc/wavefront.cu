@@ -63,18 +63,15 @@ __device__ __forceinline__ float unorm8(uint8_t b) {
     const float r = __fmaf_rn(-255.0f, q0, x);
     return __fmaf_rn(r, c, q0);
 }
-// `lut` = the 256 values of unorm8 in shared memory (k_shade fills it once per block: one LDS instead of the
-// four-instruction sequence, twelve times per textured hit), or nullptr (preview kernel).
-__device__ __forceinline__ float unorm8(uint8_t b, const float* lut) { return lut ? lut[b] : unorm8(b); }
-__device__ __forceinline__ V3 texel(const uint8_t* __restrict__ px, int w, int ch, int i, int j, const float* lut) {
+__device__ __forceinline__ V3 texel(const uint8_t* __restrict__ px, int w, int ch, int i, int j) {
     const uint8_t* p = px + ((size_t)j * w + i) * ch;
-    const float r = unorm8(__ldg(p), lut);
+    const float r = unorm8(__ldg(p));
     if (ch == 1) return v3(r, r, r);
-    const float g = unorm8(__ldg(p + 1), lut);
+    const float g = unorm8(__ldg(p + 1));
     if (ch == 2) return v3(r, g, 0.0f);
-    return v3(r, g, unorm8(__ldg(p + 2), lut));
+    return v3(r, g, unorm8(__ldg(p + 2)));
 }
-__device__ __forceinline__ V3 sample_texture(const SceneView& sc, int t, float u, float v, const float* lut = nullptr) {
+__device__ __forceinline__ V3 sample_texture(const SceneView& sc, int t, float u, float v) {
     const int w = sc.tex_w[t], h = sc.tex_h[t], ch = sc.tex_ch[t];
     if (w <= 0 || h <= 0) return v3(0.0f, 0.0f, 0.0f);
     float s = u - floorf(u);
@@ -95,117 +92,19 @@ __device__ __forceinline__ V3 sample_texture(const SceneView& sc, int t, float u
     j1 = j1 >= h ? j1 - h : j1;
     const uint8_t* px = sc.tex_px[t];
     const float w00 = (1.0f - ax) * (1.0f - ay), w10 = ax * (1.0f - ay), w01 = (1.0f - ax) * ay, w11 = ax * ay;
-    return ((texel(px, w, ch, i0, j0, lut) * w00 + texel(px, w, ch, i1, j0, lut) * w10) + texel(px, w, ch, i0, j1, lut) * w01) +
-           texel(px, w, ch, i1, j1, lut) * w11;
+    return ((texel(px, w, ch, i0, j0) * w00 + texel(px, w, ch, i1, j0) * w10) + texel(px, w, ch, i0, j1) * w01) +
+           texel(px, w, ch, i1, j1) * w11;
 }
 // S:342-368
 __device__ __forceinline__ V3 triangle_texture_color(const SceneView& sc, int numTextures, int textureIndex,
-                                                     float bw, float bu, float bv, int32_t slot,
-                                                     const float* lut = nullptr) {
+                                                     float bw, float bu, float bv, int32_t slot) {
     const float4 s0 = __ldg(&sc.tri_shade[2 * slot + 0]);
     const float4 s1 = __ldg(&sc.tri_shade[2 * slot + 1]);
     const float uvx = (s0.x * bu + s0.z * bv) + s1.x * bw;
     const float uvy = (s0.y * bu + s0.w * bv) + s1.y * bw;
     if (textureIndex < 0 || textureIndex >= numTextures) return v3(0.0f, 0.0f, 0.0f);
     if (textureIndex >= RT_MAX_TEXTURES) return v3(1.0f, 0.0f, 1.0f);
-    return sample_texture(sc, textureIndex, uvx, uvy, lut);
-}
-
-// ---- cooperative texture fetch (k_shade).  At the later bounces of the config-2 scene 5 of a warp's 32 paths hit a
-// textured triangle, and the four bilinear taps of sample_texture — address, three byte loads, three conversions and
-// the weighting, each — ran at those 5 lanes: a fifth of k_shade's instructions (ncu source view, v20).  Here the
-// textured lanes only prepare the sample (texel coordinates and weights, identical arithmetic) and hand it to the
-// warp through shared memory; lane L then fetches and weights tap L % 4 of sample L / 4, so one pass at up to 32
-// lanes serves eight samples, and every owner adds its four products in the order of the specification
-// (((t00 w00 + t10 w10) + t01 w01) + t11 w11): no bit changes.
-#ifndef RT_SHADE_COOP_TEX
-#define RT_SHADE_COOP_TEX 1
-#endif
-constexpr int kTexOwners = 8;
-struct TexJob {
-    const uint8_t* px;
-    int w, ch;
-    int i0, i1, j0, j1;
-    float w00, w10, w01, w11;
-};
-// the part of sample_texture in front of the taps; false when the texture is empty (colour 0)
-__device__ __forceinline__ bool texture_taps(const SceneView& sc, int t, float u, float v, TexJob& jb) {
-    const int w = sc.tex_w[t], h = sc.tex_h[t];
-    if (w <= 0 || h <= 0) return false;
-    float s = u - floorf(u);
-    float r = v - floorf(v);
-    if (!(s >= 0.0f && s <= 1.0f)) s = 0.0f;
-    if (!(r >= 0.0f && r <= 1.0f)) r = 0.0f;
-    const float fx = s * (float)w - 0.5f;
-    const float fy = r * (float)h - 0.5f;
-    const float flx = floorf(fx), fly = floorf(fy);
-    const float ax = fx - flx, ay = fy - fly;
-    int i0 = (int)flx, j0 = (int)fly;
-    int i1 = i0 + 1, j1 = j0 + 1;
-    jb.i0 = i0 < 0 ? i0 + w : i0;
-    jb.j0 = j0 < 0 ? j0 + h : j0;
-    jb.i1 = i1 >= w ? i1 - w : i1;
-    jb.j1 = j1 >= h ? j1 - h : j1;
-    jb.px = sc.tex_px[t];
-    jb.w = w;
-    jb.ch = sc.tex_ch[t];
-    jb.w00 = (1.0f - ax) * (1.0f - ay);
-    jb.w10 = ax * (1.0f - ay);
-    jb.w01 = (1.0f - ax) * ay;
-    jb.w11 = ax * ay;
-    return true;
-}
-// triangle_texture_color for the lanes with `want`, evaluated by the whole warp (every lane must call it)
-__device__ __forceinline__ V3 coop_texture_color(const SceneView& sc, int numTextures, bool want, int textureIndex,
-                                                 float bw, float bu, float bv, int32_t slot, TexJob* sW,
-                                                 const float* lut) {
-    constexpr uint32_t FULL = 0xffffffffu;
-    const uint32_t lane = threadIdx.x & 31u;
-    V3 color = v3(0.0f, 0.0f, 0.0f);
-    bool fetch = false;
-    TexJob jb;
-    jb.px = nullptr;
-    jb.w = jb.ch = jb.i0 = jb.i1 = jb.j0 = jb.j1 = 0;
-    jb.w00 = jb.w10 = jb.w01 = jb.w11 = 0.0f;
-    if (want) {
-        const float4 s0 = __ldg(&sc.tri_shade[2 * slot + 0]);
-        const float4 s1 = __ldg(&sc.tri_shade[2 * slot + 1]);
-        const float uvx = (s0.x * bu + s0.z * bv) + s1.x * bw;
-        const float uvy = (s0.y * bu + s0.w * bv) + s1.y * bw;
-        if (textureIndex < 0 || textureIndex >= numTextures) color = v3(0.0f, 0.0f, 0.0f);
-        else if (textureIndex >= RT_MAX_TEXTURES) color = v3(1.0f, 0.0f, 1.0f);
-        else fetch = texture_taps(sc, textureIndex, uvx, uvy, jb);
-    }
-    for (uint32_t U = __ballot_sync(FULL, fetch); U != 0u; U = __ballot_sync(FULL, fetch)) {
-        const uint32_t rank = (uint32_t)__popc(U & ((1u << lane) - 1u));
-        const bool owner = fetch && rank < (uint32_t)kTexOwners;
-        const uint32_t served = min((uint32_t)__popc(U), (uint32_t)kTexOwners);
-        if (owner) sW[rank] = jb;
-        __syncwarp();
-        V3 prod = v3(0.0f, 0.0f, 0.0f);
-        const uint32_t job = lane >> 2, tap = lane & 3u;
-        if (job < served) {
-            const TexJob J = sW[job];
-            const int i = (tap & 1u) ? J.i1 : J.i0;
-            const int j = (tap & 2u) ? J.j1 : J.j0;
-            const float wgt = tap == 0u ? J.w00 : (tap == 1u ? J.w10 : (tap == 2u ? J.w01 : J.w11));
-            prod = texel(J.px, J.w, J.ch, i, j, lut) * wgt;
-        }
-        __syncwarp();  // the slots are rewritten by the next pass
-        const uint32_t src = owner ? 4u * rank : lane;
-        V3 p[4];
-#pragma unroll
-        for (int k = 0; k < 4; k++) {
-            p[k].x = __shfl_sync(FULL, prod.x, (src + k) & 31u);
-            p[k].y = __shfl_sync(FULL, prod.y, (src + k) & 31u);
-            p[k].z = __shfl_sync(FULL, prod.z, (src + k) & 31u);
-        }
-        if (owner) {
-            color = ((p[0] + p[1]) + p[2]) + p[3];
-            fetch = false;
-        }
-    }
-    return color;
+    return sample_texture(sc, textureIndex, uvx, uvy);
 }
 
 // S:216-273
@@ -949,9 +848,13 @@ __device__ __forceinline__ BounceRandoms bounce_randoms(Rng<1>& rng, bool needDi
 // scanned in shared memory between two barriers) instead of one per warp: config 2 5604 vs 5854 Mrays/s (-4.3 %),
 // config 4 4219 vs 4280 — the atomic's cost is its latency, not the number of atomics, and a barrier adds the wait for
 // the block's slowest warp on top.  What ships is the deferred append below.
-#ifndef RT_SHADE_LUT
-#define RT_SHADE_LUT 1   // texel bytes -> float through a 256-entry shared-memory table
-#endif
+// Measured neutral and removed (profiles/r2_final_ab.txt, code in commit 38eb466): a 256-entry shared-memory table for
+// the texel byte -> float conversion (6023 vs 6056 Mrays/s) and warp-cooperative bilinear taps — the textured lanes
+// (5 of 32 at the later bounces, a fifth of k_shade's instructions) only prepare the sample and lane L fetches tap
+// L % 4 of sample L / 4 — 6056-6067 vs 6048-6058: those bounces wait on their dependent gathers, not on issue slots.
+// Also measured and removed (profiles/r2_final_ab.txt): gathering the NEXT window's hit-triangle record into L1 / L2
+// while this one is shaded (config 2 6039 / 6029 vs 6049-6059, config 4 +0.9 %), three resident blocks at 80 registers
+// without spills (6018), a smaller shade grid (32 / 16 blocks per SM: 6030 / 5981).
 #ifndef RT_SHADE_MIN_BLOCKS
 #define RT_SHADE_MIN_BLOCKS 4   // 64 registers; 5 blocks (48 registers, 358 B of spills) -15 %, 6 blocks -16 % (profiles/r2_leafmerge_shadeocc_ab.txt)
 #endif
@@ -963,12 +866,6 @@ __global__ void __launch_bounds__(kBlock, RT_SHADE_MIN_BLOCKS) k_shade(const __g
                                                   const uint32_t* __restrict__ countIn,
                                                   uint32_t* __restrict__ countOut, int bounce) {
     __shared__ CoopSlot sCoop[kBlock / 32][kCoopOwners];  // stage 2 of bounce_randoms: keys handed to the warp
-    __shared__ TexJob sTex[RT_SHADE_COOP_TEX ? kBlock / 32 : 1][kTexOwners];  // samples handed to the warp
-    __shared__ float sUnorm[RT_SHADE_LUT ? 256 : 1];  // b / 255 for every byte (exact: unorm8)
-    if (RT_SHADE_LUT && fp.u.numTextures > 0) {
-        for (int k = threadIdx.x; k < 256; k += kBlock) sUnorm[k] = unorm8((uint8_t)k);
-        __syncthreads();
-    }
     __shared__ float4 sStage[3][DEFER ? kBlock : 1];  // a lane's surviving path while the warp's queue reservation is in flight
     uint32_t pendMask = 0u, pendRaw = 0u;             // survivors of the previous window; the leader lane's atomicAdd result
     const uint32_t n = *countIn;
@@ -1020,13 +917,6 @@ __global__ void __launch_bounds__(kBlock, RT_SHADE_MIN_BLOCKS) k_shade(const __g
         rnd.d0 = rnd.d1 = 0.0f;
         if (MODE == 0 || __any_sync(FULL, needDir || nExtra > 0))
             rnd = bounce_randoms(rng, needDir, nExtra, sCoop[threadIdx.x >> 5]);
-        V3 texColor = v3(0.0f, 0.0f, 0.0f);
-        if (RT_SHADE_COOP_TEX && fp.u.numTextures > 0) {
-            const bool wantTex = valid && hslot >= 0 && m.type == RT_MAT_TEXTURE;
-            if (__any_sync(FULL, wantTex))
-                texColor = coop_texture_color(sc, fp.u.numTextures, wantTex, m.textureIndex, (1.0f - h.y) - h.z, h.y, h.z,
-                                              hslot, sTex[threadIdx.x >> 5], RT_SHADE_LUT ? sUnorm : nullptr);
-        }
         if (valid) {
             bool terminated = false;
             V3 radiance = v3(0.0f, 0.0f, 0.0f);
@@ -1047,11 +937,9 @@ __global__ void __launch_bounds__(kBlock, RT_SHADE_MIN_BLOCKS) k_shade(const __g
                         d = normalize(normal + rnd.randDir);
                         if (m.type == RT_MAT_DIFFUSE)
                             attenuation = m.color;
-                        else if (RT_SHADE_COOP_TEX)
-                            attenuation = texColor;
                         else
                             attenuation = triangle_texture_color(sc, fp.u.numTextures, m.textureIndex,
-                                                                 (1.0f - bu) - bv, bu, bv, hslot, RT_SHADE_LUT ? sUnorm : nullptr);
+                                                                 (1.0f - bu) - bv, bu, bv, hslot);
                         break;
                     }
                     case RT_MAT_SPECULAR: {
