@@ -858,7 +858,7 @@ __device__ __forceinline__ BounceRandoms bounce_randoms(Rng<1>& rng, bool needDi
 #ifndef RT_SHADE_MIN_BLOCKS
 #define RT_SHADE_MIN_BLOCKS 4   // 64 registers; 5 blocks (48 registers, 358 B of spills) -15 %, 6 blocks -16 % (profiles/r2_leafmerge_shadeocc_ab.txt)
 #endif
-template <int MODE, bool DEFER>
+template <int MODE, int DEFER>
 __global__ void __launch_bounds__(kBlock, RT_SHADE_MIN_BLOCKS) k_shade(const __grid_constant__ SceneView sc,
                                                   const __grid_constant__ FrameParams fp, PathArrays cur,
                                                   PathArrays next, const float4* __restrict__ hit,
@@ -866,11 +866,41 @@ __global__ void __launch_bounds__(kBlock, RT_SHADE_MIN_BLOCKS) k_shade(const __g
                                                   const uint32_t* __restrict__ countIn,
                                                   uint32_t* __restrict__ countOut, int bounce) {
     __shared__ CoopSlot sCoop[kBlock / 32][kCoopOwners];  // stage 2 of bounce_randoms: keys handed to the warp
-    __shared__ float4 sStage[3][DEFER ? kBlock : 1];  // a lane's surviving path while the warp's queue reservation is in flight
-    uint32_t pendMask = 0u, pendRaw = 0u;             // survivors of the previous window; the leader lane's atomicAdd result
+    // DEFER = W > 0: the survivors of W consecutive windows wait in shared memory, every lane in its own slot, while
+    // the warp's ONE queue reservation for them is in flight
+    extern __shared__ float4 sStageDyn[];  // [DEFER][3][kBlock], sized at launch (12 KB per window)
+#define sStage(k, c) sStageDyn[((k) * 3 + (c)) * kBlock + threadIdx.x]
     const uint32_t n = *countIn;
     const uint32_t lane = threadIdx.x & 31u;
     constexpr uint32_t FULL = 0xffffffffu;
+    uint32_t pend[DEFER ? DEFER : 1];  // survivor masks of the windows of the batch being staged / in flight
+#pragma unroll
+    for (int k = 0; k < (DEFER ? DEFER : 1); k++) pend[k] = 0u;
+    uint32_t pendRaw = 0u, phase = 0u;  // lane 0: the atomicAdd result; which window of the batch comes next
+    // the batch in flight goes to the queue: window k of it behind the survivors of windows 0 .. k-1
+    auto flush = [&]() {
+        uint32_t any = 0u;
+#pragma unroll
+        for (int k = 0; k < (DEFER ? DEFER : 1); k++) any |= pend[k];
+        if (any == 0u) return;
+        uint32_t at = __shfl_sync(FULL, pendRaw, 0);
+#pragma unroll
+        for (int k = 0; k < (DEFER ? DEFER : 1); k++) {
+            if ((pend[k] >> lane) & 1u) {
+                const uint32_t pos = at + __popc(pend[k] & ((1u << lane) - 1u));
+                next.od0[pos] = sStage(k, 0);
+                next.od1[pos] = sStage(k, 1);
+                next.misc[pos] = sStage(k, 2);
+            }
+            at += __popc(pend[k]);
+        }
+    };
+    auto reserve = [&]() {
+        uint32_t total = 0u;
+#pragma unroll
+        for (int k = 0; k < (DEFER ? DEFER : 1); k++) total += __popc(pend[k]);
+        if (total != 0u && lane == 0u) pendRaw = atomicAdd(countOut, total);
+    };
     for (uint32_t base = blockIdx.x * kBlock; base < n; base += gridDim.x * kBlock) {
         const uint32_t i = base + threadIdx.x;
         const bool valid = i < n;
@@ -1004,31 +1034,28 @@ __global__ void __launch_bounds__(kBlock, RT_SHADE_MIN_BLOCKS) k_shade(const __g
         }
         // compaction: the survivors of this warp take consecutive places in the next queue
         const uint32_t mask = __ballot_sync(FULL, alive);
-        if (DEFER) {
-            // Deferred append: the warp's atomicAdd on the queue counter takes microseconds to return (ncu, v19: 41.6 %
-            // of k_shade's stall samples at bounce 0 of config 2 and 44 % at every bounce of config 4 sat on the shuffle
-            // that broadcasts its result).  The survivors wait in shared memory — every lane in its OWN slot, so no
-            // synchronisation is needed — while the reservation is in flight, and are written to the queue at the end
-            // of the NEXT window, one whole iteration later.
-            if (pendMask != 0u) {
-                const uint32_t b0 = __shfl_sync(FULL, pendRaw, __ffs(pendMask) - 1);
-                if ((pendMask >> lane) & 1u) {
-                    const uint32_t pos = b0 + __popc(pendMask & ((1u << lane) - 1u));
-                    next.od0[pos] = sStage[0][threadIdx.x];
-                    next.od1[pos] = sStage[1][threadIdx.x];
-                    next.misc[pos] = sStage[2][threadIdx.x];
-                }
+        if (DEFER > 0) {
+            // Deferred append.  The warp's atomicAdd on the queue counter takes microseconds to return, and the 4.2 M of
+            // them per 133 M-path launch all hit one address (ncu, v19: 41.6 % of k_shade's stall samples at bounce 0
+            // of config 2 and 44 % at every bounce of config 4 sat on the shuffle that broadcasts the result).  So the
+            // survivors of DEFER consecutive windows share ONE reservation, issued when the last of them is staged,
+            // and are written to the queue at the end of the window after that — a whole iteration later.
+            if (phase == 0u) {
+                flush();
+#pragma unroll
+                for (int k = 0; k < DEFER; k++) pend[k] = 0u;
             }
-            pendMask = mask;
-            if (mask) {
-                if ((int)lane == __ffs(mask) - 1) pendRaw = atomicAdd(countOut, (uint32_t)__popc(mask));
-                if (alive) {
-                    sStage[0][threadIdx.x] = make_float4(o.x, o.y, o.z, d.x);
-                    sStage[1][threadIdx.x] = make_float4(d.y, d.z, rayColor.x, rayColor.y);
-                    sStage[2][threadIdx.x] = make_float4(rayColor.z, __int_as_float(slotId), __uint_as_float(carry),
-                                                         __uint_as_float(flags));
-                }
+#pragma unroll
+            for (int k = 0; k < DEFER; k++)
+                if ((uint32_t)k == phase) pend[k] = mask;
+            if (alive) {
+                sStage(phase, 0) = make_float4(o.x, o.y, o.z, d.x);
+                sStage(phase, 1) = make_float4(d.y, d.z, rayColor.x, rayColor.y);
+                sStage(phase, 2) = make_float4(rayColor.z, __int_as_float(slotId), __uint_as_float(carry),
+                                               __uint_as_float(flags));
             }
+            phase = phase + 1u == (uint32_t)DEFER ? 0u : phase + 1u;
+            if (phase == 0u) reserve();
         } else {
             uint32_t basePos = 0;
             if (mask) {
@@ -1045,16 +1072,12 @@ __global__ void __launch_bounds__(kBlock, RT_SHADE_MIN_BLOCKS) k_shade(const __g
             }
         }
     }
-    if (DEFER && pendMask != 0u) {  // the last window of this warp
-        const uint32_t b0 = __shfl_sync(FULL, pendRaw, __ffs(pendMask) - 1);
-        if ((pendMask >> lane) & 1u) {
-            const uint32_t pos = b0 + __popc(pendMask & ((1u << lane) - 1u));
-            next.od0[pos] = sStage[0][threadIdx.x];
-            next.od1[pos] = sStage[1][threadIdx.x];
-            next.misc[pos] = sStage[2][threadIdx.x];
-        }
+    if (DEFER > 0) {
+        if (phase != 0u) reserve();  // an incomplete last batch has no reservation yet
+        flush();
     }
 }
+#undef sStage
 
 __global__ void __launch_bounds__(kBlock) k_accumulate(const __grid_constant__ FrameParams fp,
                                                        const float4* __restrict__ contrib,
@@ -1423,13 +1446,29 @@ cudaError_t wf_render_batch(const Launcher& L, const SceneView& sc, const WaveBu
             // issue-active, 44 % of the stall samples) and gain 3.3-9.4 % depending on the box.
             const bool defer = L.shade_defer == 2 || (L.shade_defer == 1 && bounce == 0) ||
                                (L.shade_defer >= 3 && (bounce == 0 || fp.u.numTextures <= 0));
-#define RT_SHADE(M, D) k_shade<M, D><<<grid, kBlock, 0, L.st>>>(sc, fp, a, b, wb.hit, wb.contrib, wb.pix_rng, wb.counts + bounce, \
-                                                              wb.counts + bounce + 1, bounce)
+            // Windows per reservation: 3 (RT_SHADE_DEFER_BATCH at bounce 0, RT_SHADE_DEFER_BATCH_LATER afterwards).
+            // Measured on four boxes (profiles/r2_final_ab.txt): config 2, bounce 0 deferred, 1 / 2 / 3 / 4 windows
+            // 6059-6066 / 6077 / 6115-6128 / 6063 Mrays/s on every box; config 4, every bounce deferred, 1 window
+            // 4146 / 4410 / 4540 / 4542 depending on the box (the atomic's latency and rate are the box lottery of
+            // DESIGN.md section 6.1), 2 windows 4229 / 4257 / 4515, 3 windows 4449 / 4454 / 4461 on all of them, 4
+            // windows (48 KB of staging per block: too little L1 left) 4179.
+            const int dmode = defer ? std::max(1, std::min(3, bounce == 0 ? L.shade_defer_batch : L.shade_defer_batch_later)) : 0;
+            const size_t stage_bytes = (size_t)dmode * 3 * kBlock * sizeof(float4);
+#define RT_SHADE(M, D) k_shade<M, D><<<grid, kBlock, stage_bytes, L.st>>>(sc, fp, a, b, wb.hit, wb.contrib, wb.pix_rng, wb.counts + bounce, \
+                                                                        wb.counts + bounce + 1, bounce)
+#define RT_SHADE_M(M)                          \
+    switch (dmode) {                           \
+        case 0: RT_SHADE(M, 0); break;         \
+        case 1: RT_SHADE(M, 1); break;         \
+        case 2: RT_SHADE(M, 2); break;         \
+        default: RT_SHADE(M, 3); break;        \
+    }
             if (L.rng_mode == RT_RNG_REF_PCG) {
-                if (defer) RT_SHADE(0, true); else RT_SHADE(0, false);
+                RT_SHADE_M(0)
             } else {
-                if (defer) RT_SHADE(1, true); else RT_SHADE(1, false);
+                RT_SHADE_M(1)
             }
+#undef RT_SHADE_M
 #undef RT_SHADE
             (*L.kernel_launches)++;
         }

@@ -658,12 +658,13 @@ def test_real_asset_robot_if_generated():
 # ------------------------------------------------------------------------------------------------ round 2
 @pytest.mark.parametrize("env", [{"RT_EXT_TOP": "1"}, {"RT_HOOKS": "thread"}, {"RT_BVH_WIDTH": "2"}, {"RT_MAX_PATHS_MI": "1"},
                                  {"RT_BVH_BUILDER": "lbvh"}, {"RT_BVH_BUILDER": "lbvh", "RT_BVH_WIDTH": "2"},
-                                 {"RT_EXT_WIDEN": "1"}, {"RT_SHADE_DEFER": "0"}, {"RT_SHADE_DEFER": "2"}])
+                                 {"RT_EXT_WIDEN": "1"}, {"RT_SHADE_DEFER": "0"}, {"RT_SHADE_DEFER": "2"},
+                                 {"RT_SHADE_DEFER": "2", "RT_SHADE_DEFER_BATCH": "1", "RT_SHADE_DEFER_BATCH_LATER": "3"}])
 @pytest.mark.parametrize("rng_mode", [rt.RNG_REF_PCG, rt.RNG_PHILOX])
 def test_kernel_variants_change_no_bit(monkeypatch, env, rng_mode):
     """The shared-memory top of the tree, the per-thread hooks, the binary tree, the Karras builder, the always-widened
-    slab test, k_shade's deferred queue append (never / at every bounce; the default defers bounce 0) and a tiny path
-    budget only reorder or re-route work: frame, first-hit map and random rays must equal
+    slab test, k_shade's deferred queue append (never / at every bounce with 3 + 2 or 1 + 3 windows per reservation; the
+    default defers bounce 0) and a tiny path budget only reorder or re-route work: frame, first-hit map and random rays must equal
     the oracle bit for bit under every switch (the defaults are covered by every other test)."""
     for k, v in env.items():
         monkeypatch.setenv(k, v)
