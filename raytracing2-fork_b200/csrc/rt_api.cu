@@ -112,6 +112,7 @@ struct rt_ctx {
     int leaf_vote = 14, refill = 8, node_steps = 4;
     int node_steps_wide = 2, extend_blocks_per_sm_wide = 8;
     int use_ploc = 1, dfs_layout = 1, speculative = 1, shade_blocks_per_sm = 64;
+    int shade_defer_bounces = 1;   // RT_SHADE_DEFER_BOUNCES: with RT_SHADE_DEFER=3, a textured scene defers bounces below this
     int shade_defer_batch = 3;     // RT_SHADE_DEFER_BATCH: windows per deferred reservation at bounce 0 (1 .. 3)
     int shade_defer_batch_later = 3;  // RT_SHADE_DEFER_BATCH_LATER: ... at the later bounces
     int shade_defer = 3;           // RT_SHADE_DEFER: k_shade appends its survivors one window late (0 never, 1 bounce 0, 2 always, 3 auto)
@@ -247,6 +248,7 @@ Launcher make_launcher(rt_ctx* ctx, const rt_uniforms* u = nullptr) {
     L.shade_blocks_per_sm = ctx->shade_blocks_per_sm;
     L.shade_defer = ctx->shade_defer;
     L.shade_defer_batch = ctx->shade_defer_batch;
+    L.shade_defer_bounces = ctx->shade_defer_bounces;
     L.shade_defer_batch_later = ctx->shade_defer_batch_later;
     L.kernel_launches = &ctx->kernel_launches;
     L.extend_launches = &ctx->extend_launches;
@@ -612,6 +614,7 @@ int rt_create(rt_ctx** out, const rt_config* cfg) {
     if (const char* e1 = getenv("RT_EXT_LEAF_VOTE")) ctx->leaf_vote = std::max(1, std::min(32, atoi(e1)));
     if (const char* e2 = getenv("RT_EXT_REFILL")) ctx->refill = std::max(1, std::min(32, atoi(e2)));
     if (const char* e10 = getenv("RT_L2_PERSIST")) ctx->l2_persist = atoi(e10);
+    if (const char* e19 = getenv("RT_SHADE_DEFER_BOUNCES")) ctx->shade_defer_bounces = std::max(0, std::min(64, atoi(e19)));
     if (const char* e17 = getenv("RT_SHADE_DEFER_BATCH")) ctx->shade_defer_batch = std::max(1, std::min(3, atoi(e17)));
     if (const char* e18 = getenv("RT_SHADE_DEFER_BATCH_LATER")) ctx->shade_defer_batch_later = std::max(1, std::min(3, atoi(e18)));
     if (const char* e16 = getenv("RT_SHADE_DEFER")) ctx->shade_defer = std::max(0, std::min(3, atoi(e16)));

@@ -137,6 +137,7 @@ struct Launcher {
     bool widen_primary;  // camera rays may start far outside the quantisation grid (rt_scene.cuh, slab1)
     bool hooks_thread; // parity hooks walk the binary tree per thread instead of running k_extend
     int shade_blocks_per_sm;  // grid-stride k_shade: blocks per SM
+    int shade_defer_bounces;      // auto policy: textured scenes defer the first this-many bounces
     int shade_defer_batch;        // windows per deferred reservation at bounce 0 (1 .. 3)
     int shade_defer_batch_later;  // ... at the later bounces
     int shade_defer;          // k_shade's deferred queue append: 0 never, 1 at bounce 0, 2 at every bounce, 3 auto

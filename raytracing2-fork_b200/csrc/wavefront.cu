@@ -1445,7 +1445,7 @@ cudaError_t wf_render_batch(const Launcher& L, const SceneView& sc, const WaveBu
             // staging, those of the untextured 10 M-triangle scene wait on the atomic like bounce 0 does (34 %
             // issue-active, 44 % of the stall samples) and gain 3.3-9.4 % depending on the box.
             const bool defer = L.shade_defer == 2 || (L.shade_defer == 1 && bounce == 0) ||
-                               (L.shade_defer >= 3 && (bounce == 0 || fp.u.numTextures <= 0));
+                               (L.shade_defer >= 3 && (bounce < L.shade_defer_bounces || fp.u.numTextures <= 0));
             // Windows per reservation: 3 (RT_SHADE_DEFER_BATCH at bounce 0, RT_SHADE_DEFER_BATCH_LATER afterwards).
             // Measured on four boxes (profiles/r2_final_ab.txt): config 2, bounce 0 deferred, 1 / 2 / 3 / 4 windows
             // 6059-6066 / 6077 / 6115-6128 / 6063 Mrays/s on every box; config 4, every bounce deferred, 1 window
