@@ -821,3 +821,25 @@ def test_ray_counts_around_the_claim_size(sphere_box):
         for k in (1, 2, 3):
             assert np.array_equal(bits(got[k]), bits(ref[k][:n])), (n, k)
     be.close()
+
+
+@pytest.mark.parametrize("env", [{"RT_SHADE_DEFER": "2"},
+                                 {"RT_SHADE_DEFER": "2", "RT_SHADE_DEFER_BATCH": "2", "RT_SHADE_DEFER_BATCH_LATER": "1"},
+                                 {"RT_SHADE_DEFER": "0"}])
+def test_deferred_append_over_many_windows_per_block(monkeypatch, classic, env):
+    """k_shade's deferred append keeps up to three windows of survivors in shared memory per warp and reserves their
+    queue places with one atomic; the batches only cycle when a block shades several windows.  A one-block-per-SM shade
+    grid over a 448x448 x 2 spp frame gives every block five to eleven windows per bounce (full batches, a ragged last one, the
+    final flush; in RT_RNG_REF_PCG mode a wave holds one sample per pixel, hence the 448x448 image): the frame must
+    equal the oracle's bit for bit, in both RNG modes."""
+    scene, orc = classic
+    monkeypatch.setenv("RT_SHADE_BLOCKS_PER_SM", "1")
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    cam = rt.make_camera(448, 448, (0.0, 0.0, 15.5))
+    u = rt.screenshot_uniforms(scene, cam, spp=2, max_bounce=8, env_light=False)
+    for rng_mode in (rt.RNG_REF_PCG, rt.RNG_PHILOX):
+        be = backend(scene, rng_mode=rng_mode)
+        be.render_frame(u)
+        assert_image_equal(be.read_frame(), orc.render_frame(u, rng_mode=rng_mode), f"deferred append {env}")
+        be.close()
