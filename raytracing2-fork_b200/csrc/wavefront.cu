@@ -846,8 +846,9 @@ __device__ __forceinline__ BounceRandoms bounce_randoms(Rng<1>& rng, bool needDi
 // One bounce of S:481-560 for every live path.  `bounce` is the 0-based index of this segment.
 // Measured and not kept (profiles/r2_final_ab.txt): survivors appended with one atomicAdd per BLOCK window (warp counts
 // scanned in shared memory between two barriers) instead of one per warp: config 2 5604 vs 5854 Mrays/s (-4.3 %),
-// config 4 4219 vs 4280 — the atomic's cost is its latency, not the number of atomics, and a barrier adds the wait for
-// the block's slowest warp on top.  What ships is the deferred append below.
+// config 4 4219 vs 4280 — eight times fewer atomics, but every warp of the block then waits at two barriers for the
+// block's slowest warp AND for the atomic.  What ships is the deferred append below, which takes the wait off the
+// critical path first and then cuts the number of atomics by three without any barrier.
 // Measured neutral and removed (profiles/r2_final_ab.txt, code in commit 38eb466): a 256-entry shared-memory table for
 // the texel byte -> float conversion (6023 vs 6056 Mrays/s) and warp-cooperative bilinear taps — the textured lanes
 // (5 of 32 at the later bounces, a fifth of k_shade's instructions) only prepare the sample and lane L fetches tap
